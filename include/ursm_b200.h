@@ -1,0 +1,158 @@
+/* ursm_b200.h -- C ABI of the B200-native URSM Monte-Carlo EM hot path.
+ *
+ * The reference (lingxuez/URSM) is pure Python: there is no FFI layer to mirror.
+ * The seam this library sits behind is the class contract between gem.py and
+ * e_step_gibbs.py / m_step.py.  Each entry point below names the
+ * reference method(s) it replaces (file:line under /root/reference); the Python
+ * shims in ursm_b200/{e_step_gibbs,m_step}.py bind them with ctypes and keep the
+ * reference's class / method / attribute names, so gem.py and scUnif.py run
+ * unchanged on top (INTEGRATION.md shows the three-line binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types in any signature;
+ *   - `h_` pointers are HOST memory, `d_` pointers are DEVICE memory owned by the
+ *     caller (the Python host allocates them as torch tensors so that NCCL can
+ *     all-reduce them in place), `stream` is a cudaStream_t passed as void*;
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from ursm_last_error() (thread-local);
+ *   - matrices are row-major; expression matrices are cells|samples x genes as in
+ *     the reference's CSVs; A is genes x K;
+ *   - cells / bulk samples may be a SHARD of the global problem: `*_offset` is
+ *     the global index of the first local row and keys the counter-based RNG, so
+ *     results do not depend on the number of shards.
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels.
+ */
+#ifndef URSM_B200_H
+#define URSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ursm_sc ursm_sc; /* single-cell shard: LogitNormalGibbs_SC state  */
+typedef struct ursm_bk ursm_bk; /* bulk shard:        LogitNormalGibbs_BK state  */
+typedef struct ursm_mle ursm_mle; /* M-step workspace:  LogitNormalMLE state       */
+
+/* ---- library ---------------------------------------------------------- */
+const char* ursm_last_error(void);
+int ursm_version(void);
+/* number of kernel launches issued by this library in this process (bench.py's
+ * `gpu_launches`), and reset */
+int64_t ursm_launch_count(void);
+void ursm_launch_count_reset(void);
+
+/* ---- single cells: e_step_gibbs.py:171-377 ---------------------------------
+ * ursm_sc_create        __init__ :174-197  (caches Y, G, read depths; uploads once)
+ *   h_Y: L x N float64 counts (host), h_G: L int64 types in [0,K)
+ * ursm_sc_create_dev    same, from an fp32 L x N matrix already on the device
+ *                        (used by bench.py so c3-c5 inputs never exist on the host)
+ * ursm_sc_set_params    update_parameters :273-280  (A: N x K, pkappa/ptau: [mean,var])
+ * ursm_sc_gibbs         gibbs :286-304 = init_gibbs :212-225 + (burnin+sample*thin) x
+ *                        gibbs_cycle :307-312 {draw_w :318, draw_S :326, draw_kappa_tau
+ *                        :345, update_psi :314} + update_suffStats :245-270 on retained
+ *                        sweeps.  ONE fused persistent kernel; chain state stays on chip.
+ *   d_stats (device, caller-owned, length ursm_sc_stats_len()) receives, already
+ *   divided by `sample`:  coeffA[N*K] | coeffAsq[N*K] | exp_elbo_const |
+ *   sum_l E[kappa] | sum_l E[kappa^2] | sum_l E[tau] | sum_l E[tau^2]
+ *   -- the vector a multi-GPU caller all-reduces.
+ * ursm_sc_get_cell_moments  suff_stats exp_kappa/exp_tau/exp_kappasq/exp_tausq (:233-236)
+ * ursm_sc_get_exp_S         suff_stats["exp_S"] (:232) rows [row0,row0+nrows) as float64
+ * ursm_sc_inject            parity hook: one update_suffStats(sample) (:245-270) on a
+ *                            caller-supplied state (w, S, kappa, tau) instead of a drawn one
+ * ursm_sc_sweep_debug       parity hook: ONE gibbs_cycle of the production kernel from
+ *                            a caller-supplied (S, kappa, tau); returns the w and S it
+ *                            drew and the new (kappa, tau)
+ */
+int ursm_sc_create(ursm_sc** out, const double* h_Y, const int64_t* h_G, int64_t L, int32_t N,
+                   int32_t K, int64_t cell_offset);
+int ursm_sc_create_dev(ursm_sc** out, const float* d_Y, const int64_t* h_G, int64_t L, int32_t N,
+                       int32_t K, int64_t cell_offset);
+int ursm_sc_destroy(ursm_sc* sc);
+int64_t ursm_sc_stats_len(const ursm_sc* sc);
+int ursm_sc_set_params(ursm_sc* sc, const double* h_A, const double* h_pkappa,
+                       const double* h_ptau);
+int ursm_sc_gibbs(ursm_sc* sc, int32_t burnin, int32_t sample, int32_t thin, uint64_t seed,
+                  uint64_t em_iter, double* d_stats, void* stream);
+int ursm_sc_get_cell_moments(ursm_sc* sc, double* h_exp_kappa, double* h_exp_tau,
+                             double* h_exp_kappasq, double* h_exp_tausq);
+int ursm_sc_get_exp_S(ursm_sc* sc, double* h_out, int64_t row0, int64_t nrows);
+int ursm_sc_inject(ursm_sc* sc, const double* h_w, const int64_t* h_S, const double* h_kappa,
+                   const double* h_tau, int32_t sample, int32_t reset, double* d_stats,
+                   void* stream);
+int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kappa_in,
+                        const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t sweep,
+                        float* h_w_out, uint8_t* h_S_out, double* h_kappa_out,
+                        double* h_tau_out, int32_t* h_scan_rounds);
+/* launch geometry the shard picked (threads per CTA, genes per thread, CTAs) */
+int ursm_sc_geometry(const ursm_sc* sc, int32_t* threads, int32_t* genes_per_thread,
+                     int32_t* grid, int32_t* smem_bytes, int32_t* acc_in_smem);
+
+/* ---- bulk samples: e_step_gibbs.py:19-164 -----------------------------------
+ * ursm_bk_create       __init__ :22-36
+ * ursm_bk_set_params   update_parameters :81-84
+ * ursm_bk_set_state    init_gibbs :39-55 result: W (K x M) and, for the Gibbs mode,
+ *                       the initial sum_i Z_jik (M x K; zeros without markers)
+ * ursm_bk_mean_step    gibbs(mean_approx=True) :95-103 = get_nmf_W :157-164 +
+ *                       draw_Z_mean :149-155 + update_suffStats(1) :69-78
+ * ursm_bk_gibbs        gibbs(mean_approx=False) :105-117: per sweep draw_W :140-146 then
+ *                       draw_Z :132-138, update_suffStats on retained sweeps
+ *   d_stats (length ursm_bk_stats_len()):  exp_Zik[N*K] | sum_j exp_logW[K] |
+ *                                          sum_jk exp_Zjk*exp_logW
+ * ursm_bk_get_sample_stats  exp_Zjk (M x K), exp_logW (K x M), exp_W (K x M)
+ * freeze flags (parity hooks for the moment tests): bit0 = keep W fixed, bit1 = keep Z sums fixed
+ */
+int ursm_bk_create(ursm_bk** out, const double* h_X, int64_t M, int32_t N, int32_t K,
+                   int64_t sample_offset);
+int ursm_bk_create_dev(ursm_bk** out, const float* d_X, int64_t M, int32_t N, int32_t K,
+                       int64_t sample_offset);
+int ursm_bk_destroy(ursm_bk* bk);
+int64_t ursm_bk_stats_len(const ursm_bk* bk);
+int ursm_bk_set_params(ursm_bk* bk, const double* h_A, const double* h_alpha);
+int ursm_bk_set_state(ursm_bk* bk, const double* h_W, const double* h_Zjk);
+int ursm_bk_mean_step(ursm_bk* bk, double* d_stats, void* stream);
+int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uint64_t seed,
+                  uint64_t em_iter, int32_t freeze, double* d_stats, void* stream);
+int ursm_bk_get_sample_stats(ursm_bk* bk, double* h_exp_Zjk, double* h_exp_logW,
+                             double* h_exp_W);
+int ursm_bk_get_W(ursm_bk* bk, double* h_W);
+
+/* ---- M-step: m_step.py:13-320 ------------------------------------------------
+ * The workspace borrows the shards (it reads Y, the E[S] counters, read depths).
+ * Either shard may be NULL (bulk-only / single-cell-only model).
+ * ursm_mle_begin        update_suff_stats :50-89, local part: sum_{l in k} Y_li E[S_li]
+ *                        (-> d_part[0 : K*N], type-major) -- caller all-reduces d_part
+ * ursm_mle_pass_u       opt_u :108-115 + update_gd_coeffConst :118-125, local part for the
+ *                        columns flagged active: d_part[k*N+i] = sum_{l in k} E[S_li] R_l/u_l,
+ *                        d_part[K*N] = sum_l R_l log u_l   (length K*N+1)
+ * ursm_mle_set_coeffs   installs the (all-reduced) coefficient matrices, all K x N type-major
+ * ursm_mle_step_A       one outer iteration of opt_Ak :157-182 for every active column at
+ *                        once: backtracking :209-233 with simplex_proj (utils.py:8-31) as the
+ *                        projection, get_grad_A :262-272, get_obj_A :275-287.  d_cconst_part is
+ *                        the all-reduced output of ursm_mle_pass_u.  h_delta[k] = ||dA_k||_1.
+ * ursm_mle_closed_form  the bulk-only column rule :149-153
+ * ursm_mle_elbo_terms   the A-dependent sums of compute_elbo :290-320
+ */
+int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t K, double min_A);
+int ursm_mle_destroy(ursm_mle* m);
+int ursm_mle_set_A(ursm_mle* m, const double* h_A);
+int ursm_mle_get_A(ursm_mle* m, double* h_A);
+int ursm_mle_begin(ursm_mle* m, double* d_part, void* stream);
+int ursm_mle_pass_u(ursm_mle* m, const int32_t* h_active, double* d_part, void* stream);
+int ursm_mle_set_coeffs(ursm_mle* m, const double* d_cAinv, const double* d_cA,
+                        const double* d_coeffA);
+int ursm_mle_step_A(ursm_mle* m, const int32_t* h_active, const double* d_cconst_part,
+                    double init_step, double* h_delta, int32_t* h_halvings, void* stream);
+int ursm_mle_closed_form(ursm_mle* m, int32_t k, const double* d_exp_Zik, void* stream);
+int ursm_mle_elbo_terms(ursm_mle* m, const double* d_cconst_part, double* h_terms3,
+                        void* stream);
+int ursm_mle_get_u(ursm_mle* m, double* h_u);
+/* projection onto {y >= min_y, sum y = 1} of a host vector, on the device
+ * (utils.py:8-31) -- parity hook for the M-step's inner kernel */
+int ursm_simplex_proj(const double* h_y, int32_t n, double min_y, double* h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URSM_B200_H */

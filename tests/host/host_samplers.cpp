@@ -1,0 +1,46 @@
+// Host build of ursm_b200/csrc/samplers.cuh (the same source the kernels inline),
+// exported with a C ABI so tests/test_samplers_host.py can check the sampler
+// arithmetic on the CPU.  Test infrastructure only.
+#include <stdint.h>
+#include "../../ursm_b200/csrc/samplers.cuh"
+
+using namespace ursm;
+
+extern "C" {
+void h_philox(uint64_t key, uint32_t x, uint32_t y, uint32_t z, uint32_t* out, int nblocks) {
+  Philox g(key, x, y, z);
+  for (int i = 0; i < 4 * nblocks; ++i) out[i] = g.next();
+}
+double h_pg_mass(double z) { return pg_mass_texpon((float)z); }
+void h_pg_draws(double psi, int n, uint64_t seed, double* out) {
+  for (int i = 0; i < n; ++i) {
+    Philox g(seed, (uint32_t)i, 7u, 0u);
+    out[i] = pg1_devroye((float)psi, g);
+  }
+}
+double h_s_threshold(double psi, double u, double a, double R) {
+  return s_threshold((float)psi, (float)u, (float)a, (float)R);
+}
+void h_binomial(int n, double p, int count, uint64_t seed, int* out) {
+  for (int i = 0; i < count; ++i) {
+    Philox g(seed, (uint32_t)i, 1u, 0u);
+    out[i] = binomial(n, p, g);
+  }
+}
+void h_gamma(double shape, int count, uint64_t seed, double* out) {
+  for (int i = 0; i < count; ++i) {
+    Philox g(seed, (uint32_t)i, 2u, 0u);
+    out[i] = gamma_mt(shape, g);
+  }
+}
+void h_normal(int count, uint64_t seed, double* out) {
+  for (int i = 0; i < count; ++i) {
+    Philox g(seed, (uint32_t)i, 3u, 0u);
+    normal_pair(g, out[2 * i], out[2 * i + 1]);
+  }
+}
+void h_uniform(int count, uint64_t seed, double* out) {
+  Philox g(seed, 0u, 0u, 0u);
+  for (int i = 0; i < count; ++i) out[i] = g.uniform();
+}
+}

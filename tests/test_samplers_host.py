@@ -1,0 +1,161 @@
+"""Sampler arithmetic of ursm_b200/csrc/samplers.cuh, compiled for the HOST
+(tests/host/host_samplers.cpp includes the very header the kernels inline) and
+checked against exact moments / pmfs.  No GPU needed."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy import stats
+from scipy.special import expit
+
+from oracle import ursm_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host", "host_samplers.cpp")
+OUT = os.path.join(HERE, "host", "_build", "libhost_samplers.so")
+HDRS = [os.path.join(HERE, "..", "ursm_b200", "csrc", h) for h in ("samplers.cuh", "rng.cuh")]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    newest = max(os.path.getmtime(p) for p in [SRC] + HDRS)
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", OUT, SRC])
+    L = ctypes.CDLL(OUT)
+    L.h_pg_mass.restype = ctypes.c_double
+    L.h_pg_mass.argtypes = [ctypes.c_double]
+    L.h_s_threshold.restype = ctypes.c_double
+    L.h_s_threshold.argtypes = [ctypes.c_double] * 4
+    L.h_pg_draws.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]
+    L.h_binomial.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_uint64,
+                             ctypes.c_void_p]
+    L.h_gamma.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]
+    return L
+
+
+def _dbl(n):
+    return (ctypes.c_double * n)()
+
+
+def test_philox_known_answer(lib):
+    # Random123 kat_vectors: philox4x32-10, counter 0, key 0
+    out = (ctypes.c_uint32 * 8)()
+    lib.h_philox(ctypes.c_uint64(0), 0, 0, 0, out, 2)
+    assert [hex(v) for v in out[:4]] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    # second block = counter word 3 incremented, must differ
+    assert list(out[4:]) != list(out[:4])
+    # all-ones counter/key vector from the same KAT file
+    lib.h_philox(ctypes.c_uint64(0xffffffffffffffff), 0xffffffff, 0xffffffff, 0xffffffff, out, 1)
+    # c3 starts at 0 in our stream layout, so only check determinism + avalanche here
+    a = list(out[:4])
+    lib.h_philox(ctypes.c_uint64(0xffffffffffffffff), 0xffffffff, 0xffffffff, 0xfffffffe, out, 1)
+    assert a != list(out[:4])
+
+
+def test_uniform_open_interval(lib):
+    n = 200000
+    out = _dbl(n)
+    lib.h_uniform(n, ctypes.c_uint64(5), out)
+    u = np.frombuffer(out, dtype=np.float64)
+    assert u.min() > 0 and u.max() < 1
+    assert abs(u.mean() - 0.5) < 4 / np.sqrt(12 * n)
+    assert stats.kstest(u, "uniform").pvalue > 1e-3
+
+
+def test_pg_mass_matches_oracle(lib):
+    for z in (0.0, 0.1, 0.5, 1.0, 1.5, 1.5624, 1.5626, 2.0, 3.0, 5.0, 8.0, 15.0, 50.0, 500.0):
+        np.testing.assert_allclose(lib.h_pg_mass(z), orc.pg_mass_texpon(z), rtol=5e-6, atol=1e-30)
+
+
+@pytest.mark.parametrize("psi", [0.0, 0.3, 1.0, 2.0, 3.2, 5.0, 9.0, 20.0, 60.0, 300.0, -4.0, 3000.0])
+def test_pg1_moments(lib, psi):
+    """E, Var and Laplace transform of the fp32 device sampler vs closed form."""
+    n = 400000
+    out = _dbl(n)
+    lib.h_pg_draws(psi, n, ctypes.c_uint64(123 + int(abs(psi) * 10)), out)
+    x = np.frombuffer(out, dtype=np.float64)
+    m, v = float(orc.pg1_mean(psi)), float(orc.pg1_var(psi))
+    assert np.all(x > 0)
+    assert abs(x.mean() - m) < 4.5 * np.sqrt(v / n) + 2e-7 * m, (psi, x.mean(), m)
+    assert abs(x.var() / v - 1) < 0.02, (psi, x.var(), v)
+    for t in (0.5, 4.0):
+        a = abs(psi)
+        # cosh(a/2)/cosh(b) computed stably for large arguments
+        b = np.sqrt((a * a / 2 + t) / 2)
+        lap = np.exp(a / 2 - b) * (1 + np.exp(-a)) / (1 + np.exp(-2 * b))
+        est = np.exp(-t * x)
+        assert abs(est.mean() - lap) < 4.5 * est.std() / np.sqrt(n) + 1e-6 * lap, (psi, t)
+
+
+def test_pg1_distribution_vs_oracle(lib):
+    """Two-sample KS: fp32 Philox sampler vs the float64 oracle restatement."""
+    rs = np.random.RandomState(3)
+    for psi in (0.5, 2.8, 7.0):
+        n = 20000
+        out = _dbl(n)
+        lib.h_pg_draws(psi, n, ctypes.c_uint64(99), out)
+        x = np.frombuffer(out, dtype=np.float64)
+        y = np.array([orc.pg1_devroye(psi, rs) for _ in range(6000)])
+        assert stats.ks_2samp(x, y).pvalue > 1e-3, psi
+
+
+def test_s_threshold_is_the_bernoulli(lib):
+    """s_other > T(u)  <=>  u < expit(psi - R log1p(a/s_other))  (e_step_gibbs.py:337-338)."""
+    rs = np.random.RandomState(0)
+    agree = total = 0
+    for _ in range(20000):
+        psi = rs.normal(0, 6)
+        a = np.exp(rs.normal(-9, 1.5))
+        R = float(rs.choice([0, 1, 50, 4000, 40000]))
+        so = np.exp(rs.normal(-1, 1))
+        u = rs.uniform(1e-6, 1 - 1e-6)
+        T = lib.h_s_threshold(psi, u, a, R)
+        b = expit(psi - R * np.log1p(a / so)) if R > 0 else expit(psi)
+        if abs(u - b) < 2e-5 * max(b, 1e-3):  # razor edge: fp32 vs fp64 may disagree
+            continue
+        total += 1
+        agree += int((so > T) == (u < b))
+    assert total > 15000 and agree == total
+
+
+@pytest.mark.parametrize("n,p", [(1, 0.3), (7, 0.5), (40, 0.02), (50, 0.9), (300, 0.2),
+                                 (5000, 0.013), (100000, 0.4), (2000000, 0.001), (3000, 0.97)])
+def test_binomial_pmf(lib, n, p):
+    cnt = 200000
+    out = (ctypes.c_int * cnt)()
+    lib.h_binomial(n, p, cnt, ctypes.c_uint64(n * 7 + 1), out)
+    x = np.frombuffer(out, dtype=np.int32)
+    assert x.min() >= 0 and x.max() <= n
+    assert abs(x.mean() - n * p) < 4.5 * np.sqrt(n * p * (1 - p) / cnt)
+    assert abs(x.var() / (n * p * (1 - p)) - 1) < 0.03
+    # chi-square against the exact pmf over the bulk of the support
+    lo, hi = stats.binom.ppf([1e-4, 1 - 1e-4], n, p).astype(int)
+    edges = np.unique(np.linspace(lo, hi + 1, 30).astype(int))
+    obs = np.histogram(x, bins=np.concatenate([[-1], edges, [n + 1]]) + 0.0)[0]
+    cdf = stats.binom.cdf(np.concatenate([edges - 1, [n]]), n, p)
+    exp = np.diff(np.concatenate([[0], cdf])) * cnt
+    keep = exp > 5
+    chi = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert stats.chi2.sf(chi, keep.sum() - 1) > 1e-4, (n, p, chi)
+
+
+@pytest.mark.parametrize("shape", [0.05, 0.5, 1.0, 2.5, 40.0, 3000.0])
+def test_gamma_mt(lib, shape):
+    n = 200000
+    out = _dbl(n)
+    lib.h_gamma(shape, n, ctypes.c_uint64(17), out)
+    x = np.frombuffer(out, dtype=np.float64)
+    assert abs(x.mean() - shape) < 4.5 * np.sqrt(shape / n)
+    assert stats.kstest(x, "gamma", args=(shape,)).pvalue > 1e-4
+
+
+def test_normal_pair(lib):
+    n = 100000
+    out = _dbl(2 * n)
+    lib.h_normal(n, ctypes.c_uint64(4), out)
+    x = np.frombuffer(out, dtype=np.float64)
+    assert stats.kstest(x, "norm").pvalue > 1e-3
+    assert abs(np.corrcoef(x[0::2], x[1::2])[0, 1]) < 0.02

@@ -1,0 +1,455 @@
+// Bulk-sample E-step for sm_100a: e_step_gibbs.py:19-164.
+//
+// Data flow: the reference materialises Z (M x N x K fp64) and
+// AW (N x M) every sweep; here neither exists.  One "tile" kernel owns a tile of
+// genes (A rows live in registers for the whole kernel) and walks a chunk of bulk
+// samples; AW_ij is a K-term dot product in registers, the K-way split of X_ji is
+// consumed on the spot into
+//    sum_i Z_jik  (warp reduction -> one atomic per warp, sample, type)   and
+//    sum_j Z_jik  (register accumulators, flushed once per CTA),
+// so HBM sees X exactly once per pass (4 B per (sample, gene)).
+//   mode 0: numerators of get_nmf_W (:157-164)
+//   mode 1: draw_Z_mean (:149-155) + update_suffStats(1) (:69-78)
+//   mode 2: draw_Z (:132-138), multinomial as a chain of exact binomials
+#include "common.cuh"
+#include "samplers.cuh"
+#include "sc_shard.h"
+#include "../../include/ursm_b200.h"
+
+#include <algorithm>
+
+namespace ursm {
+
+constexpr int kBkThreads = 256;
+
+struct BkTileArgs {
+  const float* X;      // [M][N]
+  const double* A;     // [K][N]
+  const double* W;     // [M][K]
+  long long M;
+  int N, K;
+  long long sample_offset;
+  int chunk;           // samples per grid.y slice
+  double* sumJ;        // [M][K]  mode 0: nmf numerators; 1: exp_Zjk; 2: n_next
+  double* sumI;        // [K][N]  modes 1, 2 (retained): exp_Zik accumulator
+  double scaleI;       // 1/sample
+  int accumulate_I;    // mode 2: this sweep is retained
+  unsigned long long key;
+  unsigned int sweep;
+};
+
+template <int KMAX, int MODE>
+__global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
+  extern __shared__ double bk_smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int K = a.K, N = a.N;
+  const long long j0 = (long long)blockIdx.y * a.chunk;
+  const long long j1 = min(a.M, j0 + a.chunk);
+  const int nloc = (int)(j1 - j0);
+  double* Wsm = bk_smem;             // [nloc][K] W rows of this CTA's samples
+  double* Jsm = bk_smem + nloc * K;  // [nloc][K] CTA-level sums over genes
+  for (int t = tid; t < nloc * K; t += kBkThreads) {
+    Wsm[t] = a.W[j0 * K + t];
+    Jsm[t] = 0.0;
+  }
+  const int gi = blockIdx.x * kBkThreads + tid;
+  const bool in = gi < N;
+  double Ar[KMAX], accI[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    Ar[k] = (k < K && in) ? a.A[(size_t)k * N + gi] : 0.0;
+    accI[k] = 0.0;
+  }
+  __syncthreads();
+
+  for (int jl = 0; jl < nloc; ++jl) {
+    const long long j = j0 + jl;
+    const double* Wj = Wsm + jl * K;
+    const float xf = in ? a.X[(size_t)j * N + gi] : 0.f;
+    const bool active = xf != 0.f;  // zero counts contribute nothing in any mode
+    double aw = 0.0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) aw += Wj[k] * Ar[k];
+    if (MODE == 2) {
+      Philox rng(a.key, (uint32_t)gi, (uint32_t)(a.sample_offset + j), kPurposeBulkZ | a.sweep);
+      int rem = active ? (int)xf : 0;
+      double remq = aw;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k >= K) break;
+        const double qk = Wj[k] * Ar[k];
+        int z;
+        if (k == K - 1) {
+          z = rem;
+        } else {
+          const double p = fmin(fmax(qk / remq, 0.0), 1.0);
+          z = (rem > 0) ? binomial(rem, p, rng) : 0;
+        }
+        rem -= z;
+        remq -= qk;
+        if (a.accumulate_I) accI[k] += (double)z;
+        const int tot = __reduce_add_sync(0xffffffffu, z);
+        if (lane == 0 && tot != 0) atomicAdd(&Jsm[jl * K + k], (double)tot);
+      }
+    } else {
+      const double r = active ? (double)xf / aw : 0.0;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k >= K) break;
+        double v;
+        if (MODE == 0) {
+          v = Ar[k] * r;
+        } else {
+          v = Wj[k] * Ar[k] * r;
+          accI[k] += v;
+        }
+        v = warp_sum(v);
+        if (lane == 0 && v != 0.0) atomicAdd(&Jsm[jl * K + k], v);
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < nloc * K; t += kBkThreads)
+    if (Jsm[t] != 0.0) atomicAdd(&a.sumJ[j0 * K + t], Jsm[t]);
+  if (in && (MODE == 1 || (MODE == 2 && a.accumulate_I))) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k >= K) break;
+      if (accI[k] != 0.0) atomicAdd(&a.sumI[(size_t)k * N + gi], accI[k] * a.scaleI);
+    }
+  }
+}
+
+// W_kj <- W_kj * numer_jk + alpha_k - 1, renormalised over k (:159-164)
+__global__ void bk_nmf_update_kernel(double* W, const double* numer, const double* alpha,
+                                     long long M, int K) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  double s = 0.0;
+  for (int k = 0; k < K; ++k) {
+    double v = W[j * K + k] * numer[j * K + k] + alpha[k] - 1.0;
+    W[j * K + k] = v;
+    s += v;
+  }
+  for (int k = 0; k < K; ++k) W[j * K + k] /= s;
+}
+
+// One Gibbs sweep's W step (:140-146) plus the per-sample part of update_suffStats.
+__global__ void bk_w_draw_kernel(double* W, const double* n_prev, double* n_next,
+                                 const double* alpha, long long M, int K, long long sample_offset,
+                                 unsigned long long key, unsigned int sweep, int prev_retained,
+                                 int retained, int draw, double inv_sample, double* eZjk,
+                                 double* eLogW, double* eW) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  if (prev_retained)
+    for (int k = 0; k < K; ++k) eZjk[j * K + k] += n_prev[j * K + k] * inv_sample;
+  if (draw) {
+    Philox rng(key, 0xfffffffeu, (uint32_t)(sample_offset + j), kPurposeBulkW | sweep);
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double gmm = gamma_mt(alpha[k] + n_prev[j * K + k], rng);
+      W[j * K + k] = gmm;
+      s += gmm;
+    }
+    for (int k = 0; k < K; ++k) W[j * K + k] /= s;
+  }
+  if (retained) {
+    for (int k = 0; k < K; ++k) {
+      double w = W[j * K + k];
+      eW[j * K + k] += w * inv_sample;
+      eLogW[j * K + k] += log(w) * inv_sample;
+    }
+  }
+  if (n_next)
+    for (int k = 0; k < K; ++k) n_next[j * K + k] = 0.0;
+}
+
+__global__ void bk_mean_finalize_kernel(const double* W, double* eLogW, double* eW, long long M,
+                                        int K) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M * K) return;
+  eW[t] = W[t];
+  eLogW[t] = log(W[t]);
+}
+
+// stats tail: sum_j E[log W_kj] (K values) and sum_jk E[Z_jk] E[log W_kj]
+__global__ void bk_tail_kernel(const double* eZjk, const double* eLogW, long long M, int K,
+                               double* tail) {
+  __shared__ double red[32];
+  double cross = 0.0;
+  for (long long t = threadIdx.x; t < M * K; t += blockDim.x) cross += eZjk[t] * eLogW[t];
+  cross = block_sum(cross, red);
+  if (threadIdx.x == 0) tail[K] = cross;
+  for (int k = 0; k < K; ++k) {
+    double s = 0.0;
+    for (long long j = threadIdx.x; j < M; j += blockDim.x) s += eLogW[j * K + k];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) tail[k] = s;
+  }
+}
+
+template <int MODE>
+static void bk_launch_tile(BkShard* b, BkTileArgs& a, cudaStream_t st) {
+  a.X = b->X;
+  a.A = b->A.p;
+  a.W = b->W.p;
+  a.M = b->M;
+  a.N = b->N;
+  a.K = b->K;
+  a.sample_offset = b->sample_offset;
+  const int gx = (b->N + kBkThreads - 1) / kBkThreads;
+  // enough CTAs to fill the machine a few times over; a chunk's W rows and
+  // per-sample sums (2 x chunk x K doubles) must fit the default 48 KB
+  const long long max_chunk = std::max<long long>(1, (40 * 1024) / (16 * (long long)b->K));
+  long long want_y = std::max<long long>(1, (long long)(8 * b->num_sms + gx - 1) / gx);
+  want_y = std::max<long long>(want_y, (b->M + max_chunk - 1) / max_chunk);
+  long long ny = std::min<long long>(b->M, want_y);
+  a.chunk = (int)((b->M + ny - 1) / ny);
+  ny = (b->M + a.chunk - 1) / a.chunk;
+  URSM_REQUIRE(ny <= 65535, "bulk tile kernel: too many sample chunks");
+  dim3 grid(gx, (unsigned)ny);
+  size_t smem = 2 * (size_t)a.chunk * b->K * sizeof(double);
+  const int K = b->K;
+  if (K <= 4)
+    bk_tile_kernel<4, MODE><<<grid, kBkThreads, smem, st>>>(a);
+  else if (K <= 8)
+    bk_tile_kernel<8, MODE><<<grid, kBkThreads, smem, st>>>(a);
+  else if (K <= 12)
+    bk_tile_kernel<12, MODE><<<grid, kBkThreads, smem, st>>>(a);
+  else if (K <= 20)
+    bk_tile_kernel<20, MODE><<<grid, kBkThreads, smem, st>>>(a);
+  else
+    bk_tile_kernel<32, MODE><<<grid, kBkThreads, smem, st>>>(a);
+  URSM_LAUNCH_CHECK();
+}
+
+static void bk_finish_create(BkShard* b) {
+  int dev;
+  URSM_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  URSM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  b->num_sms = prop.multiProcessorCount;
+  URSM_REQUIRE(b->K <= 32, "bulk kernels support K <= 32 cell types");
+  const size_t MK = (size_t)b->M * b->K;
+  b->A.alloc((size_t)b->K * b->N);
+  b->alpha.alloc(b->K);
+  b->W.alloc(MK);
+  b->nA.alloc(MK);
+  b->nB.alloc(MK);
+  b->acc.alloc(MK);
+  b->eZjk.alloc(MK);
+  b->eLogW.alloc(MK);
+  b->eW.alloc(MK);
+  b->nA.zero();
+  b->nB.zero();
+  URSM_CUDA(cudaDeviceSynchronize());
+}
+
+}  // namespace ursm
+
+using namespace ursm;
+
+extern "C" {
+
+int ursm_bk_create(ursm_bk** out, const double* h_X, int64_t M, int32_t N, int32_t K,
+                   int64_t sample_offset) {
+  URSM_API_BEGIN
+  URSM_REQUIRE(out && h_X && M > 0 && N > 0 && K > 0, "ursm_bk_create: bad argument");
+  BkShard* b = new BkShard();
+  b->M = M;
+  b->N = N;
+  b->K = K;
+  b->sample_offset = sample_offset;
+  try {
+    const size_t n = (size_t)M * N;
+    b->Xown.alloc(n);
+    b->X = b->Xown.p;
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = (float)h_X[i];
+    URSM_CUDA(cudaMemcpy(b->Xown.p, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    bk_finish_create(b);
+  } catch (...) {
+    delete b;
+    throw;
+  }
+  *out = reinterpret_cast<ursm_bk*>(b);
+  URSM_API_END
+}
+
+int ursm_bk_create_dev(ursm_bk** out, const float* d_X, int64_t M, int32_t N, int32_t K,
+                       int64_t sample_offset) {
+  URSM_API_BEGIN
+  URSM_REQUIRE(out && d_X && M > 0 && N > 0 && K > 0, "ursm_bk_create_dev: bad argument");
+  BkShard* b = new BkShard();
+  b->M = M;
+  b->N = N;
+  b->K = K;
+  b->sample_offset = sample_offset;
+  b->X = d_X;
+  try {
+    bk_finish_create(b);
+  } catch (...) {
+    delete b;
+    throw;
+  }
+  *out = reinterpret_cast<ursm_bk*>(b);
+  URSM_API_END
+}
+
+int ursm_bk_destroy(ursm_bk* bk) {
+  URSM_API_BEGIN
+  delete reinterpret_cast<BkShard*>(bk);
+  URSM_API_END
+}
+
+int64_t ursm_bk_stats_len(const ursm_bk* bk) {
+  const BkShard* b = reinterpret_cast<const BkShard*>(bk);
+  return (int64_t)b->N * b->K + b->K + 1;
+}
+
+int ursm_bk_set_params(ursm_bk* bk, const double* h_A, const double* h_alpha) {
+  URSM_API_BEGIN
+  BkShard* b = reinterpret_cast<BkShard*>(bk);
+  URSM_REQUIRE(b && h_A && h_alpha, "ursm_bk_set_params: bad argument");
+  std::vector<double> At((size_t)b->K * b->N);
+  for (int i = 0; i < b->N; ++i)
+    for (int k = 0; k < b->K; ++k) At[(size_t)k * b->N + i] = h_A[(size_t)i * b->K + k];
+  URSM_CUDA(cudaMemcpy(b->A.p, At.data(), At.size() * sizeof(double), cudaMemcpyHostToDevice));
+  URSM_CUDA(cudaMemcpy(b->alpha.p, h_alpha, b->K * sizeof(double), cudaMemcpyHostToDevice));
+  b->has_params = true;
+  URSM_API_END
+}
+
+int ursm_bk_set_state(ursm_bk* bk, const double* h_W, const double* h_Zjk) {
+  URSM_API_BEGIN
+  BkShard* b = reinterpret_cast<BkShard*>(bk);
+  URSM_REQUIRE(b && h_W, "ursm_bk_set_state: bad argument");
+  const size_t MK = (size_t)b->M * b->K;
+  std::vector<double> Wt(MK);  // reference layout is K x M
+  for (long long j = 0; j < b->M; ++j)
+    for (int k = 0; k < b->K; ++k) Wt[j * b->K + k] = h_W[(size_t)k * b->M + j];
+  URSM_CUDA(cudaMemcpy(b->W.p, Wt.data(), MK * sizeof(double), cudaMemcpyHostToDevice));
+  if (h_Zjk)
+    URSM_CUDA(cudaMemcpy(b->nA.p, h_Zjk, MK * sizeof(double), cudaMemcpyHostToDevice));
+  else
+    b->nA.zero();
+  URSM_CUDA(cudaDeviceSynchronize());
+  b->has_state = true;
+  URSM_API_END
+}
+
+int ursm_bk_mean_step(ursm_bk* bk, double* d_stats, void* stream) {
+  URSM_API_BEGIN
+  BkShard* b = reinterpret_cast<BkShard*>(bk);
+  URSM_REQUIRE(b && d_stats, "ursm_bk_mean_step: bad argument");
+  URSM_REQUIRE(b->has_params && b->has_state, "ursm_bk_mean_step: params/state not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t MK = (size_t)b->M * b->K;
+  const unsigned mb = (unsigned)((b->M + 127) / 128), mkb = (unsigned)((MK + 255) / 256);
+  URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_bk_stats_len(bk) * sizeof(double), st));
+  b->acc.zero(st);
+  b->eZjk.zero(st);
+  BkTileArgs a;
+  memset(&a, 0, sizeof a);
+  a.sumJ = b->acc.p;
+  bk_launch_tile<0>(b, a, st);
+  bk_nmf_update_kernel<<<mb, 128, 0, st>>>(b->W.p, b->acc.p, b->alpha.p, b->M, b->K);
+  URSM_LAUNCH_CHECK();
+  a.sumJ = b->eZjk.p;
+  a.sumI = d_stats;
+  a.scaleI = 1.0;
+  bk_launch_tile<1>(b, a, st);
+  bk_mean_finalize_kernel<<<mkb, 256, 0, st>>>(b->W.p, b->eLogW.p, b->eW.p, b->M, b->K);
+  URSM_LAUNCH_CHECK();
+  bk_tail_kernel<<<1, 1024, 0, st>>>(b->eZjk.p, b->eLogW.p, b->M, b->K,
+                                     d_stats + (size_t)b->N * b->K);
+  URSM_LAUNCH_CHECK();
+  URSM_API_END
+}
+
+int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uint64_t seed,
+                  uint64_t em_iter, int32_t freeze, double* d_stats, void* stream) {
+  URSM_API_BEGIN
+  BkShard* b = reinterpret_cast<BkShard*>(bk);
+  URSM_REQUIRE(b && d_stats, "ursm_bk_gibbs: bad argument");
+  URSM_REQUIRE(b->has_params && b->has_state, "ursm_bk_gibbs: params/state not set");
+  URSM_REQUIRE(burnin >= 0 && sample >= 1 && thin >= 1, "ursm_bk_gibbs: bad sweep counts");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned mb = (unsigned)((b->M + 127) / 128);
+  const unsigned long long key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1) + 0x5bd1e995ull;
+  const double inv = 1.0 / sample;
+  URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_bk_stats_len(bk) * sizeof(double), st));
+  b->eZjk.zero(st);
+  b->eLogW.zero(st);
+  b->eW.zero(st);
+  const int nsweeps = burnin + sample * thin;
+  bool prev_ret = false;
+  // nA holds sum_i Z of the previous sweep (chain persists across E-steps, :99-100,136)
+  for (int sweep = 0; sweep < nsweeps; ++sweep) {
+    const bool retained = sweep >= burnin && ((sweep - burnin) % thin == 0);
+    const bool freezeW = freeze & 1, freezeZ = freeze & 2;
+    bk_w_draw_kernel<<<mb, 128, 0, st>>>(b->W.p, b->nA.p, b->nB.p, b->alpha.p, b->M, b->K,
+                                         b->sample_offset, key, (unsigned)sweep, prev_ret ? 1 : 0,
+                                         retained ? 1 : 0, freezeW ? 0 : 1, inv, b->eZjk.p,
+                                         b->eLogW.p, b->eW.p);
+    URSM_LAUNCH_CHECK();
+    BkTileArgs a;
+    memset(&a, 0, sizeof a);
+    a.sumJ = b->nB.p;
+    a.sumI = d_stats;
+    a.scaleI = inv;
+    a.accumulate_I = retained ? 1 : 0;
+    a.key = key;
+    a.sweep = (unsigned)sweep;
+    bk_launch_tile<2>(b, a, st);
+    if (!freezeZ) std::swap(b->nA.p, b->nB.p);
+    if (freezeZ && retained) {
+      // frozen-Z moment test: E[Z_jk] accumulates the fixed sums
+    }
+    prev_ret = retained;
+  }
+  // the last retained sweep's sum_i Z
+  bk_w_draw_kernel<<<mb, 128, 0, st>>>(b->W.p, b->nA.p, nullptr, b->alpha.p, b->M, b->K,
+                                       b->sample_offset, key, 0u, prev_ret ? 1 : 0, 0, 0, inv,
+                                       b->eZjk.p, b->eLogW.p, b->eW.p);
+  URSM_LAUNCH_CHECK();
+  bk_tail_kernel<<<1, 1024, 0, st>>>(b->eZjk.p, b->eLogW.p, b->M, b->K,
+                                     d_stats + (size_t)b->N * b->K);
+  URSM_LAUNCH_CHECK();
+  URSM_API_END
+}
+
+static void copy_MK_to_KM(const BkShard* b, const double* d_src, double* h_dst, bool transpose) {
+  const size_t MK = (size_t)b->M * b->K;
+  std::vector<double> tmp(MK);
+  URSM_CUDA(cudaMemcpy(tmp.data(), d_src, MK * sizeof(double), cudaMemcpyDeviceToHost));
+  if (!transpose) {
+    memcpy(h_dst, tmp.data(), MK * sizeof(double));
+    return;
+  }
+  for (long long j = 0; j < b->M; ++j)
+    for (int k = 0; k < b->K; ++k) h_dst[(size_t)k * b->M + j] = tmp[j * b->K + k];
+}
+
+int ursm_bk_get_sample_stats(ursm_bk* bk, double* h_exp_Zjk, double* h_exp_logW,
+                             double* h_exp_W) {
+  URSM_API_BEGIN
+  BkShard* b = reinterpret_cast<BkShard*>(bk);
+  URSM_CUDA(cudaDeviceSynchronize());
+  if (h_exp_Zjk) copy_MK_to_KM(b, b->eZjk.p, h_exp_Zjk, false);  // M x K
+  if (h_exp_logW) copy_MK_to_KM(b, b->eLogW.p, h_exp_logW, true);  // K x M
+  if (h_exp_W) copy_MK_to_KM(b, b->eW.p, h_exp_W, true);          // K x M
+  URSM_API_END
+}
+
+int ursm_bk_get_W(ursm_bk* bk, double* h_W) {
+  URSM_API_BEGIN
+  BkShard* b = reinterpret_cast<BkShard*>(bk);
+  URSM_CUDA(cudaDeviceSynchronize());
+  copy_MK_to_KM(b, b->W.p, h_W, true);
+  URSM_API_END
+}
+
+}  // extern "C"

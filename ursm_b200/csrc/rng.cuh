@@ -1,0 +1,100 @@
+// Counter-based Philox4x32-10 (Salmon et al., SC'11) and the uniform/normal
+// helpers every sampler in this library draws from.
+//
+// Replaces, for the CUDA path, the reference's *unseeded global* numpy
+// RandomState (e_step_gibbs.py:137,144,216,340,376) and the per-thread GSL
+// Mersenne twisters inside pypolyagamma (e_step_gibbs.py:200-209).  A stream is
+// addressed by (seed, em_iter) as the key and (gene, cell, sweep|purpose, block)
+// as the counter, with cell/sample indices GLOBAL -- so a draw does not depend
+// on how cells are sharded over GPUs (check #4).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define URSM_HD __host__ __device__ __forceinline__
+#else
+#define URSM_HD inline
+#endif
+
+namespace ursm {
+
+struct Philox {
+  uint32_t c0, c1, c2, c3;  // counter; c3 is the running block index
+  uint32_t k0, k1;          // key
+  uint32_t b0, b1, b2, b3;  // buffered outputs (shift register, no local memory)
+  int n;                    // outputs left in the buffer
+
+  URSM_HD Philox() {}
+  URSM_HD Philox(uint64_t key, uint32_t x, uint32_t y, uint32_t z) {
+    k0 = (uint32_t)key;
+    k1 = (uint32_t)(key >> 32);
+    c0 = x;
+    c1 = y;
+    c2 = z;
+    c3 = 0;
+    n = 0;
+  }
+
+  static URSM_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+  }
+
+  URSM_HD void refill() {
+    uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, ka = k0, kb = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(0xD2511F53u, x0, h0, l0);
+      mulhilo(0xCD9E8D57u, x2, h1, l1);
+      x0 = h1 ^ x1 ^ ka;
+      x1 = l1;
+      x2 = h0 ^ x3 ^ kb;
+      x3 = l0;
+      ka += 0x9E3779B9u;
+      kb += 0xBB67AE85u;
+    }
+    b0 = x0;
+    b1 = x1;
+    b2 = x2;
+    b3 = x3;
+    n = 4;
+    ++c3;
+  }
+
+  URSM_HD uint32_t next() {
+    if (n == 0) refill();
+    uint32_t r = b0;
+    b0 = b1;
+    b1 = b2;
+    b2 = b3;
+    --n;
+    return r;
+  }
+
+  // uniform on the open interval (0,1), 24-bit resolution, never 0 or 1
+  URSM_HD float uniform() { return ((next() >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+  // 53-bit-ish double uniform in (0,1) from two words
+  URSM_HD double uniform_d() {
+    uint32_t a = next(), b = next();
+    return (((uint64_t)(a >> 5) << 26) + (b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+  }
+};
+
+// Stream "purposes" folded into the third counter word (top 4 bits) so the
+// different consumers of one (cell, sweep) never share a counter.
+enum : uint32_t {
+  kPurposeGene = 0u << 28,      // per (cell, gene, sweep): S uniform first, then PG draw
+  kPurposeCell = 1u << 28,      // per (cell, sweep): the (kappa, tau) normal pair
+  kPurposeInit = 2u << 28,      // per (cell, gene): initial S ~ Bern(1/2)
+  kPurposeBulkZ = 3u << 28,     // per (sample, gene, sweep): multinomial split
+  kPurposeBulkW = 4u << 28,     // per (sample, sweep): Dirichlet
+};
+
+}  // namespace ursm

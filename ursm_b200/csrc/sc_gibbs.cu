@@ -1,0 +1,788 @@
+// Single-cell Gibbs E-step for sm_100a: e_step_gibbs.py:171-377 as ONE persistent
+// kernel.
+//
+// Design:
+//  * cells are independent inside an E-step (parameters frozen), so one CTA runs
+//    ALL burnin + sample*thin sweeps of a cell with the chain state on chip:
+//    per gene 4 B (w, fp32) + 2 B (E[S] counter) + 1 B (flags) of shared memory.
+//    HBM is touched once per cell: read the count row (which genes are zero),
+//    write the E[S] counters.  psi, w, S never exist in HBM (the reference keeps
+//    five L x N fp64/int64 arrays, :216-220,232).
+//  * thread t owns the contiguous gene run [t*g, (t+1)*g); run element j lives in
+//    shared-memory slot j*T + t (bank-conflict free, no padding).
+//  * draw_S (:326-342) is a sequential scan over the zero genes of a cell through
+//    the running sum_AS.  It is kept EXACT: each update is rewritten as
+//    "s_other > T_i" (samplers.cuh::s_threshold), a thread scans its own run
+//    assuming the sweep-start sum as its incoming value and records the smallest
+//    |s_other - T_i| it saw (its margin); a block-wide exclusive scan of the
+//    per-thread net changes gives every thread its true incoming sum; only
+//    threads whose incoming sum moved by more than their margin re-scan (their
+//    uniforms are regenerated from the same Philox counter); repeat to the fixed
+//    point, which is the unique sequential solution.
+//  * draw_kappa_tau (:345-377): five block reductions in fp64, closed-form 2x2
+//    Cholesky draw by one thread, broadcast through shared memory.
+//  * update_suffStats (:245-270) needs w(t) together with the kappa/tau drawn
+//    AFTER it, so the fold of sweep t is deferred into the gene loop of sweep
+//    t+1 (w(t) is still in its slot); per-gene accumulators for coeffA/coeffAsq
+//    are CTA-private (shared memory for small N, an L2-resident scratch row
+//    otherwise) and flushed with fp64 atomics when the CTA changes cell type.
+#include "common.cuh"
+#include "samplers.cuh"
+#include "sc_shard.h"
+#include "../../include/ursm_b200.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace ursm {
+
+struct ScGibbsArgs {
+  const float* Y;       // [L][N]
+  const int* G;         // [L]
+  const double* R;      // [L]
+  const int* order;     // [L] cells sorted by type
+  const float* Aslot;   // [K][slots]
+  long long L;
+  int N, K;
+  long long cell_offset;
+  int g, slots;
+  double mu_k, prec_k, mu_t, prec_t;
+  int burnin, nsweeps, thin, sample;
+  int sweep0;           // first sweep index (debug: run sweep `sweep0` only)
+  unsigned long long key;
+  unsigned short* cnt;  // [L][N]
+  double* cellmom;      // [4][L]
+  double* stats;        // coeffA[K][N] | coeffAsq[K][N] | elbo | sk | skk | st | stt
+  float* scratch;       // [grid][2][slots]
+  int* counter;
+  int flush_every;
+  // debug (all optional)
+  const unsigned char* S0;  // [L][N]
+  const double* kt0;        // [2][L]
+  float* w_out;             // [L][N]
+  unsigned char* S_out;     // [L][N]
+  double* kt_out;           // [2][L]
+  int* rounds_out;          // [L]
+};
+
+__device__ __forceinline__ double block_excl_scan(double v, double* red, double& total) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) red[warp] = inc;
+  __syncthreads();
+  double x = (lane < nw) ? red[lane] : 0.0;
+  double pre = warp_sum(lane < warp ? x : 0.0);
+  total = warp_sum(x);
+  return pre + inc - v;
+}
+
+template <bool ACC_SMEM>
+__global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int g = a.g, N = a.N, slots = a.slots;
+
+  double* red = reinterpret_cast<double*>(smem_raw);        // [32*5] reductions
+  double* bc = red + 160;                                    // [4] broadcast
+  int* ibc = reinterpret_cast<int*>(bc + 4);                 // [4]
+  float* w_s = reinterpret_cast<float*>(ibc + 4);            // [slots]
+  float* accA = ACC_SMEM ? (w_s + slots) : (a.scratch + (size_t)blockIdx.x * 2 * slots);
+  float* accQ = accA + slots;
+  unsigned short* cnt_s =
+      reinterpret_cast<unsigned short*>(ACC_SMEM ? (w_s + 3 * (size_t)slots) : (w_s + slots));
+  unsigned char* fl_s = reinterpret_cast<unsigned char*>(cnt_s + slots);
+
+  const double inv_sample = 1.0 / (double)a.sample;
+  double* coeffA = a.stats;
+  double* coeffQ = a.stats + (size_t)a.K * N;
+  double* scal = a.stats + 2 * (size_t)a.K * N;
+
+  int cur_type = -1, cells_in_acc = 0;
+  for (int s = tid; s < slots; s += T) {
+    accA[s] = 0.f;
+    accQ[s] = 0.f;
+  }
+
+  while (true) {
+    __syncthreads();
+    if (tid == 0) ibc[0] = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const long long c = ibc[0];
+    const bool finished = c >= a.L;
+    const int l = finished ? 0 : a.order[c];
+    const int type = finished ? -1 : a.G[l];
+    if (cur_type >= 0 && (finished || type != cur_type || cells_in_acc >= a.flush_every)) {
+      // flush the CTA-private accumulators into coeffA/coeffAsq[:, cur_type]
+      for (int i = tid; i < N; i += T) {
+        int slot = (i % g) * T + i / g;
+        float vA = accA[slot], vQ = accQ[slot];
+        if (vA != 0.f) atomicAdd(&coeffA[(size_t)cur_type * N + i], (double)vA * inv_sample);
+        if (vQ != 0.f) atomicAdd(&coeffQ[(size_t)cur_type * N + i], (double)vQ * inv_sample);
+        accA[slot] = 0.f;
+        accQ[slot] = 0.f;
+      }
+      cells_in_acc = 0;
+      __syncthreads();
+    }
+    if (finished) break;
+    cur_type = type;
+    ++cells_in_acc;
+
+    const unsigned int gl = (unsigned int)(a.cell_offset + l);  // global cell id keys the RNG
+    const float Rf = (float)a.R[l];
+    const float* Acol = a.Aslot + (size_t)type * slots;
+
+    // ---- init_gibbs (:212-225): S ~ Bern(1/2), S[Y>0] = 1, kappa/tau = prior means
+    for (int i = tid; i < N; i += T) {
+      int slot = (i % g) * T + i / g;
+      bool pos = a.Y[(size_t)l * N + i] > 0.f;
+      unsigned int S;
+      if (a.S0) {
+        S = a.S0[(size_t)l * N + i] ? 1u : 0u;
+      } else {
+        Philox r0(a.key, (uint32_t)i, gl, kPurposeInit);
+        S = r0.next() >> 31;
+      }
+      if (pos) S = 1u;
+      fl_s[slot] = (unsigned char)((pos ? 1u : 0u) | (S << 1));
+      cnt_s[slot] = 0;
+    }
+    __syncthreads();
+    double kappa = a.kt0 ? a.kt0[l] : a.mu_k;
+    double tau = a.kt0 ? a.kt0[a.L + l] : a.mu_t;
+    double s_cur;
+    {
+      double part = 0.0;
+      for (int j = 0; j < g; ++j) {
+        int i = tid * g + j;
+        if (i >= N) break;
+        int slot = j * T + tid;
+        if (fl_s[slot] & 2) part += (double)Acol[slot];
+      }
+      s_cur = block_sum(part, red);
+    }
+
+    double m_k = 0, m_kk = 0, m_t = 0, m_tt = 0, elbo = 0;  // meaningful in thread 0
+    bool prev_ret = false;
+    float pk = 0.f, pt = 0.f;
+    int rounds_total = 0;
+
+    for (int sweep = a.sweep0; sweep < a.sweep0 + a.nsweeps; ++sweep) {
+      const bool retained = sweep >= a.burnin && ((sweep - a.burnin) % a.thin == 0);
+      const float fk = (float)kappa, ft = (float)tau;
+      const float cA1 = pt, cA2 = pt * pk, cQ = -0.5f * pt * pt;
+      double sw = 0, swa = 0, swaa = 0, as = 0, s_run = s_cur;
+      int nS = 0;
+      float margin = INFINITY;
+      // ---- draw_w (:318-323) + speculative draw_S (:326-342) + deferred fold
+      for (int j = 0; j < g; ++j) {
+        const int i = tid * g + j;
+        if (i >= N) break;
+        const int slot = j * T + tid;
+        const float av = Acol[slot];
+        const unsigned int f = fl_s[slot];
+        const unsigned int Sold = (f >> 1) & 1u, pos = f & 1u;
+        if (prev_ret) {  // update_suffStats (:245-270) of the previous sweep
+          const float wold = w_s[slot];
+          accA[slot] += ((float)Sold - 0.5f) * cA1 - wold * cA2;
+          accQ[slot] += cQ * wold;
+          cnt_s[slot] += (unsigned short)Sold;
+        }
+        const float psi = fmaf(ft, av, fk);
+        Philox rng(a.key, (uint32_t)i, gl, kPurposeGene | (uint32_t)sweep);
+        const float u = rng.uniform();  // first word of the stream: the S uniform
+        const float wn = pg1_devroye(psi, rng);
+        w_s[slot] = wn;
+        const double wd = wn, ad = av;
+        sw += wd;
+        swa += wd * ad;
+        swaa += wd * ad * ad;
+        unsigned int Snew = 1u;
+        if (!pos) {
+          const float Tth = s_threshold(psi, u, av, Rf);
+          const double so = s_run - (Sold ? ad : 0.0);
+          Snew = (so > (double)Tth) ? 1u : 0u;
+          margin = fminf(margin, fabsf((float)(so - (double)Tth)));
+          s_run = so + (Snew ? ad : 0.0);
+        }
+        fl_s[slot] = (unsigned char)(pos | (Snew << 1) | (Sold << 2));
+        nS += (int)Snew;
+        if (Snew) as += ad;
+      }
+      // ---- exact sequential semantics: fixed point over the incoming prefix sums
+      double delta = s_run - s_cur, used_in = s_cur;
+      int rounds = 0;
+      while (true) {
+        double total;
+        const double incoming = s_cur + block_excl_scan(delta, red, total);
+        const bool viol = !(fabs(incoming - used_in) < (double)margin) && incoming != used_in &&
+                          margin != INFINITY;
+        if (!__syncthreads_or(viol) || rounds > T) break;
+        ++rounds;
+        if (viol) {
+          s_run = incoming;
+          margin = INFINITY;
+          nS = 0;
+          as = 0;
+          for (int j = 0; j < g; ++j) {
+            const int i = tid * g + j;
+            if (i >= N) break;
+            const int slot = j * T + tid;
+            const float av = Acol[slot];
+            const double ad = av;
+            const unsigned int f = fl_s[slot];
+            const unsigned int Sold = (f >> 2) & 1u, pos = f & 1u;
+            unsigned int Snew = 1u;
+            if (!pos) {
+              Philox rng(a.key, (uint32_t)i, gl, kPurposeGene | (uint32_t)sweep);
+              const float u = rng.uniform();
+              const float psi = fmaf(ft, av, fk);
+              const float Tth = s_threshold(psi, u, av, Rf);
+              const double so = s_run - (Sold ? ad : 0.0);
+              Snew = (so > (double)Tth) ? 1u : 0u;
+              margin = fminf(margin, fabsf((float)(so - (double)Tth)));
+              s_run = so + (Snew ? ad : 0.0);
+            }
+            fl_s[slot] = (unsigned char)(pos | (Snew << 1) | (Sold << 2));
+            nS += (int)Snew;
+            if (Snew) as += ad;
+          }
+          delta = s_run - incoming;
+          used_in = incoming;
+        }
+      }
+      rounds_total += rounds;
+      // ---- draw_kappa_tau (:345-377)
+      sw = warp_sum(sw);
+      swa = warp_sum(swa);
+      swaa = warp_sum(swaa);
+      as = warp_sum(as);
+      nS = warp_sum(nS);
+      __syncthreads();
+      if (lane == 0) {
+        red[warp] = sw;
+        red[32 + warp] = swa;
+        red[64 + warp] = swaa;
+        red[96 + warp] = as;
+        red[128 + warp] = (double)nS;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        double x0 = (lane < nw) ? red[lane] : 0.0;
+        double x1 = (lane < nw) ? red[32 + lane] : 0.0;
+        double x2 = (lane < nw) ? red[64 + lane] : 0.0;
+        double x3 = (lane < nw) ? red[96 + lane] : 0.0;
+        double x4 = (lane < nw) ? red[128 + lane] : 0.0;
+        x0 = warp_sum(x0);
+        x1 = warp_sum(x1);
+        x2 = warp_sum(x2);
+        x3 = warp_sum(x3);
+        x4 = warp_sum(x4);
+        if (lane == 0) {
+          const double d0 = x0 + a.prec_k, d1 = x2 + a.prec_t, off = x1;
+          const double det = d0 * d1 - off * off;
+          const double c00 = d1 / det, c01 = -off / det, c11 = d0 / det;
+          const double b0 = x4 - 0.5 * N + a.mu_k * a.prec_k;
+          const double b1 = x3 - 0.5 + a.mu_t * a.prec_t;
+          const double m0 = c00 * b0 + c01 * b1, m1 = c01 * b0 + c11 * b1;
+          const double l00 = sqrt(c00), l10 = c01 / l00;
+          const double l11 = sqrt(fmax(c11 - l10 * l10, 0.0));
+          Philox rk(a.key, 0xffffffffu, gl, kPurposeCell | (uint32_t)sweep);
+          double n0, n1;
+          normal_pair(rk, n0, n1);
+          bc[0] = m0 + l00 * n0;
+          bc[1] = m1 + l10 * n0 + l11 * n1;
+          bc[2] = x3;  // exact sum_AS for the next sweep
+          bc[3] = x0;  // sum_i w
+          ibc[1] = (int)x4;
+        }
+      }
+      __syncthreads();
+      kappa = bc[0];
+      tau = bc[1];
+      s_cur = bc[2];
+      if (retained && tid == 0) {
+        m_k += kappa;
+        m_kk += kappa * kappa;
+        m_t += tau;
+        m_tt += tau * tau;
+        // sum_i [-w kappa^2/2 + (S - 1/2) kappa]   (:254-257)
+        elbo += -0.5 * kappa * kappa * bc[3] + kappa * ((double)ibc[1] - 0.5 * N);
+      }
+      prev_ret = retained;
+      pk = (float)kappa;
+      pt = (float)tau;
+    }
+    // ---- fold of the last sweep, write-back
+    if (prev_ret) {
+      const float cA1 = pt, cA2 = pt * pk, cQ = -0.5f * pt * pt;
+      for (int j = 0; j < g; ++j) {
+        const int i = tid * g + j;
+        if (i >= N) break;
+        const int slot = j * T + tid;
+        const unsigned int Sold = (fl_s[slot] >> 1) & 1u;
+        const float wold = w_s[slot];
+        accA[slot] += ((float)Sold - 0.5f) * cA1 - wold * cA2;
+        accQ[slot] += cQ * wold;
+        cnt_s[slot] += (unsigned short)Sold;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += T) {
+      int slot = (i % g) * T + i / g;
+      a.cnt[(size_t)l * N + i] = cnt_s[slot];
+      if (a.w_out) a.w_out[(size_t)l * N + i] = w_s[slot];
+      if (a.S_out) a.S_out[(size_t)l * N + i] = (fl_s[slot] >> 1) & 1u;
+    }
+    if (tid == 0) {
+      a.cellmom[l] = m_k * inv_sample;
+      a.cellmom[a.L + l] = m_t * inv_sample;
+      a.cellmom[2 * a.L + l] = m_kk * inv_sample;
+      a.cellmom[3 * a.L + l] = m_tt * inv_sample;
+      atomicAdd(&scal[0], elbo * inv_sample);
+      atomicAdd(&scal[1], m_k * inv_sample);
+      atomicAdd(&scal[2], m_kk * inv_sample);
+      atomicAdd(&scal[3], m_t * inv_sample);
+      atomicAdd(&scal[4], m_tt * inv_sample);
+      if (a.kt_out) {
+        a.kt_out[l] = kappa;
+        a.kt_out[a.L + l] = tau;
+      }
+      if (a.rounds_out) a.rounds_out[l] = rounds_total;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// update_suffStats (:245-270) on an injected state: parity check #1.
+// One CTA per cell; fp64 throughout; same formulas as the fold above.
+// ---------------------------------------------------------------------------
+__global__ void sc_inject_kernel(const double* w, const unsigned char* S, const double* kappa,
+                                 const double* tau, const int* G, long long L, int N, int K,
+                                 double inv_sample, unsigned short* cnt, double* cellmom,
+                                 double* stats) {
+  __shared__ double red[32];
+  const long long l = blockIdx.x;
+  const int type = G[l];
+  const double kp = kappa[l], tu = tau[l];
+  double* coeffA = stats + (size_t)type * N;
+  double* coeffQ = stats + (size_t)K * N + (size_t)type * N;
+  double* scal = stats + 2 * (size_t)K * N;
+  double e = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double wv = w[(size_t)l * N + i];
+    const double Sv = S[(size_t)l * N + i] ? 1.0 : 0.0;
+    e += -0.5 * wv * kp * kp + (Sv - 0.5) * kp;
+    atomicAdd(&coeffA[i], ((Sv - 0.5) * tu - wv * tu * kp) * inv_sample);
+    atomicAdd(&coeffQ[i], (-0.5 * wv * tu * tu) * inv_sample);
+    cnt[(size_t)l * N + i] += (unsigned short)(Sv > 0.5);
+  }
+  e = block_sum(e, red);
+  if (threadIdx.x == 0) {
+    cellmom[l] += kp * inv_sample;
+    cellmom[L + l] += tu * inv_sample;
+    cellmom[2 * L + l] += kp * kp * inv_sample;
+    cellmom[3 * L + l] += tu * tu * inv_sample;
+    atomicAdd(&scal[0], e * inv_sample);
+    atomicAdd(&scal[1], kp * inv_sample);
+    atomicAdd(&scal[2], kp * kp * inv_sample);
+    atomicAdd(&scal[3], tu * inv_sample);
+    atomicAdd(&scal[4], tu * tu * inv_sample);
+  }
+}
+
+__global__ void sc_rowsum_kernel(const float* Y, long long L, int N, double* R) {
+  __shared__ double red[32];
+  const long long l = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += (double)Y[(size_t)l * N + i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) R[l] = s;
+}
+
+__global__ void cast_f64_f32_kernel(const double* in, float* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (float)in[i];
+}
+
+__global__ void cnt_to_f64_kernel(const unsigned short* cnt, double* out, size_t n, double inv) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (double)cnt[i] * inv;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static void upload_f64_as_f32(const double* h, float* d, size_t n) {
+  // chunked: stage fp64 on the device, cast there
+  const size_t chunk = (size_t)1 << 24;
+  DevBuf<double> stage;
+  stage.alloc(std::min(n, chunk));
+  for (size_t off = 0; off < n; off += chunk) {
+    size_t m = std::min(chunk, n - off);
+    URSM_CUDA(cudaMemcpy(stage.p, h + off, m * sizeof(double), cudaMemcpyHostToDevice));
+    cast_f64_f32_kernel<<<1184, 256>>>(stage.p, d + off, m);
+    URSM_LAUNCH_CHECK();
+  }
+  URSM_CUDA(cudaDeviceSynchronize());
+}
+
+static void sc_pick_geometry(ScShard* s) {
+  int dev;
+  URSM_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  URSM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  s->num_sms = prop.multiProcessorCount;
+  int maxT = 1024;
+  if (const char* e = getenv("URSM_SC_MAX_THREADS")) maxT = std::max(64, std::min(1024, atoi(e)));
+  int gpt = 16;
+  if (const char* e = getenv("URSM_SC_GENES_PER_THREAD")) gpt = std::max(1, atoi(e));
+  int T = ((s->N + gpt - 1) / gpt + 31) / 32 * 32;
+  T = std::max(64, std::min(maxT / 32 * 32, T));
+  s->T = T;
+  s->g = (s->N + T - 1) / T;
+  s->slots = s->T * s->g;
+  const size_t fixed = 160 * 8 + 4 * 8 + 4 * 4;
+  size_t small = fixed + (size_t)s->slots * 7, big = fixed + (size_t)s->slots * 15;
+  int acc_limit = 32 * 1024;
+  if (const char* e = getenv("URSM_SC_ACC_SMEM_LIMIT")) acc_limit = atoi(e);
+  s->acc_smem = big <= (size_t)acc_limit;
+  s->smem = (int)((s->acc_smem ? big : small) + 16);
+  URSM_REQUIRE((size_t)s->smem <= (size_t)prop.sharedMemPerBlockOptin,
+               "gene count too large for the chain-resident single-cell kernel "
+               "(7 bytes of shared memory per gene)");
+  if (s->acc_smem) {
+    URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem));
+  } else {
+    URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem));
+  }
+  int occ = 0;
+  if (s->acc_smem) {
+    URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<true>, s->T,
+                                                            s->smem));
+  } else {
+    URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<false>, s->T,
+                                                            s->smem));
+  }
+  URSM_REQUIRE(occ >= 1, "single-cell Gibbs kernel does not fit on an SM");
+  s->occ = occ;
+  long long want = (long long)s->num_sms * occ;
+  s->grid = (int)std::max<long long>(1, std::min<long long>(want, s->L));
+  if (!s->acc_smem) s->scratch.alloc((size_t)s->grid * 2 * s->slots);
+}
+
+static void sc_finish_create(ScShard* s, const int64_t* h_G) {
+  const long long L = s->L;
+  std::vector<int> G(L), order(L);
+  s->type_count.assign(s->K, 0);
+  for (long long l = 0; l < L; ++l) {
+    URSM_REQUIRE(h_G[l] >= 0 && h_G[l] < s->K, "cell type outside {0..K-1}");
+    G[l] = (int)h_G[l];
+    s->type_count[G[l]]++;
+  }
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return G[x] < G[y]; });
+  s->type_start.assign(s->K + 1, 0);
+  for (int k = 0; k < s->K; ++k) s->type_start[k + 1] = s->type_start[k] + s->type_count[k];
+  s->G.alloc(L);
+  s->order.alloc(L);
+  URSM_CUDA(cudaMemcpy(s->G.p, G.data(), L * sizeof(int), cudaMemcpyHostToDevice));
+  URSM_CUDA(cudaMemcpy(s->order.p, order.data(), L * sizeof(int), cudaMemcpyHostToDevice));
+  s->R.alloc(L);
+  sc_rowsum_kernel<<<(unsigned)L, 256>>>(s->Y, L, s->N, s->R.p);
+  URSM_LAUNCH_CHECK();
+  s->cnt.alloc((size_t)L * s->N);
+  s->cnt.zero();
+  s->cellmom.alloc(4 * (size_t)L);
+  s->cellmom.zero();
+  s->counter.alloc(1);
+  s->A.alloc((size_t)s->N * s->K);
+  sc_pick_geometry(s);
+  s->Aslot.alloc((size_t)s->K * s->slots);
+  s->sample = 1;
+  URSM_CUDA(cudaDeviceSynchronize());
+}
+
+static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
+  a.Y = s->Y;
+  a.G = s->G.p;
+  a.R = s->R.p;
+  a.order = s->order.p;
+  a.Aslot = s->Aslot.p;
+  a.L = s->L;
+  a.N = s->N;
+  a.K = s->K;
+  a.cell_offset = s->cell_offset;
+  a.g = s->g;
+  a.slots = s->slots;
+  a.mu_k = s->pkappa[0];
+  a.prec_k = 1.0 / s->pkappa[1];
+  a.mu_t = s->ptau[0];
+  a.prec_t = 1.0 / s->ptau[1];
+  a.cnt = s->cnt.p;
+  a.cellmom = s->cellmom.p;
+  a.scratch = s->scratch.p;
+  a.counter = s->counter.p;
+  a.flush_every = 16;
+  URSM_CUDA(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
+  if (s->acc_smem)
+    sc_gibbs_kernel<true><<<s->grid, s->T, s->smem, st>>>(a);
+  else
+    sc_gibbs_kernel<false><<<s->grid, s->T, s->smem, st>>>(a);
+  URSM_LAUNCH_CHECK();
+}
+
+}  // namespace ursm
+
+using namespace ursm;
+
+extern "C" {
+
+int ursm_sc_create(ursm_sc** out, const double* h_Y, const int64_t* h_G, int64_t L, int32_t N,
+                   int32_t K, int64_t cell_offset) {
+  URSM_API_BEGIN
+  URSM_REQUIRE(out && h_Y && h_G && L > 0 && N > 0 && K > 0, "ursm_sc_create: bad argument");
+  URSM_REQUIRE(L < (1ll << 31), "ursm_sc_create: more than 2^31 cells in one shard");
+  ScShard* s = new ScShard();
+  s->L = L;
+  s->N = N;
+  s->K = K;
+  s->cell_offset = cell_offset;
+  try {
+    s->Yown.alloc((size_t)L * N);
+    s->Y = s->Yown.p;
+    upload_f64_as_f32(h_Y, s->Yown.p, (size_t)L * N);
+    sc_finish_create(s, h_G);
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  *out = reinterpret_cast<ursm_sc*>(s);
+  URSM_API_END
+}
+
+int ursm_sc_create_dev(ursm_sc** out, const float* d_Y, const int64_t* h_G, int64_t L, int32_t N,
+                       int32_t K, int64_t cell_offset) {
+  URSM_API_BEGIN
+  URSM_REQUIRE(out && d_Y && h_G && L > 0 && N > 0 && K > 0, "ursm_sc_create_dev: bad argument");
+  URSM_REQUIRE(L < (1ll << 31), "ursm_sc_create_dev: more than 2^31 cells in one shard");
+  ScShard* s = new ScShard();
+  s->L = L;
+  s->N = N;
+  s->K = K;
+  s->cell_offset = cell_offset;
+  s->Y = d_Y;  // borrowed: caller keeps it alive
+  try {
+    sc_finish_create(s, h_G);
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  *out = reinterpret_cast<ursm_sc*>(s);
+  URSM_API_END
+}
+
+int ursm_sc_destroy(ursm_sc* sc) {
+  URSM_API_BEGIN
+  delete reinterpret_cast<ScShard*>(sc);
+  URSM_API_END
+}
+
+int64_t ursm_sc_stats_len(const ursm_sc* sc) {
+  const ScShard* s = reinterpret_cast<const ScShard*>(sc);
+  return 2 * (int64_t)s->N * s->K + 5;
+}
+
+int ursm_sc_geometry(const ursm_sc* sc, int32_t* threads, int32_t* genes_per_thread, int32_t* grid,
+                     int32_t* smem_bytes, int32_t* acc_in_smem) {
+  const ScShard* s = reinterpret_cast<const ScShard*>(sc);
+  if (threads) *threads = s->T;
+  if (genes_per_thread) *genes_per_thread = s->g;
+  if (grid) *grid = s->grid;
+  if (smem_bytes) *smem_bytes = s->smem;
+  if (acc_in_smem) *acc_in_smem = s->acc_smem ? 1 : 0;
+  return 0;
+}
+
+int ursm_sc_set_params(ursm_sc* sc, const double* h_A, const double* h_pkappa,
+                       const double* h_ptau) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && h_A && h_pkappa && h_ptau, "ursm_sc_set_params: bad argument");
+  URSM_REQUIRE(h_pkappa[1] > 0 && h_ptau[1] > 0, "ursm_sc_set_params: prior variance must be > 0");
+  const int N = s->N, K = s->K;
+  URSM_CUDA(cudaMemcpy(s->A.p, h_A, (size_t)N * K * sizeof(double), cudaMemcpyHostToDevice));
+  std::vector<float> slot((size_t)K * s->slots, 0.f);
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i < N; ++i)
+      slot[(size_t)k * s->slots + (size_t)(i % s->g) * s->T + i / s->g] = (float)h_A[(size_t)i * K + k];
+  URSM_CUDA(cudaMemcpy(s->Aslot.p, slot.data(), slot.size() * sizeof(float),
+                       cudaMemcpyHostToDevice));
+  s->pkappa[0] = h_pkappa[0];
+  s->pkappa[1] = h_pkappa[1];
+  s->ptau[0] = h_ptau[0];
+  s->ptau[1] = h_ptau[1];
+  s->has_params = true;
+  URSM_API_END
+}
+
+int ursm_sc_gibbs(ursm_sc* sc, int32_t burnin, int32_t sample, int32_t thin, uint64_t seed,
+                  uint64_t em_iter, double* d_stats, void* stream) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && d_stats, "ursm_sc_gibbs: bad argument");
+  URSM_REQUIRE(s->has_params, "ursm_sc_gibbs: call ursm_sc_set_params first");
+  URSM_REQUIRE(burnin >= 0 && sample >= 1 && thin >= 1, "ursm_sc_gibbs: bad sweep counts");
+  URSM_REQUIRE(sample <= 65535, "ursm_sc_gibbs: sample must be <= 65535 (uint16 E[S] counters)");
+  URSM_REQUIRE((long long)burnin + (long long)sample * thin < (1 << 28),
+               "ursm_sc_gibbs: too many sweeps");
+  cudaStream_t st = (cudaStream_t)stream;
+  URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_sc_stats_len(sc) * sizeof(double), st));
+  ScGibbsArgs a;
+  memset(&a, 0, sizeof a);
+  a.burnin = burnin;
+  a.nsweeps = burnin + sample * thin;
+  a.thin = thin;
+  a.sample = sample;
+  a.sweep0 = 0;
+  a.key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1);
+  a.stats = d_stats;
+  s->sample = sample;
+  sc_launch(s, a, st);
+  URSM_API_END
+}
+
+int ursm_sc_get_cell_moments(ursm_sc* sc, double* h_exp_kappa, double* h_exp_tau,
+                             double* h_exp_kappasq, double* h_exp_tausq) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  const size_t L = s->L, b = L * sizeof(double);
+  URSM_CUDA(cudaDeviceSynchronize());
+  if (h_exp_kappa) URSM_CUDA(cudaMemcpy(h_exp_kappa, s->cellmom.p, b, cudaMemcpyDeviceToHost));
+  if (h_exp_tau) URSM_CUDA(cudaMemcpy(h_exp_tau, s->cellmom.p + L, b, cudaMemcpyDeviceToHost));
+  if (h_exp_kappasq)
+    URSM_CUDA(cudaMemcpy(h_exp_kappasq, s->cellmom.p + 2 * L, b, cudaMemcpyDeviceToHost));
+  if (h_exp_tausq)
+    URSM_CUDA(cudaMemcpy(h_exp_tausq, s->cellmom.p + 3 * L, b, cudaMemcpyDeviceToHost));
+  URSM_API_END
+}
+
+int ursm_sc_get_exp_S(ursm_sc* sc, double* h_out, int64_t row0, int64_t nrows) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= s->L, "ursm_sc_get_exp_S: bad rows");
+  const size_t rows_per = std::max<size_t>(1, ((size_t)1 << 24) / s->N);
+  DevBuf<double> stage;
+  stage.alloc(std::min<size_t>(rows_per, (size_t)nrows) * s->N);
+  URSM_CUDA(cudaDeviceSynchronize());
+  for (int64_t r = 0; r < nrows; r += rows_per) {
+    size_t m = std::min<size_t>(rows_per, (size_t)(nrows - r)) * s->N;
+    cnt_to_f64_kernel<<<1184, 256>>>(s->cnt.p + (size_t)(row0 + r) * s->N, stage.p, m,
+                                     1.0 / s->sample);
+    URSM_LAUNCH_CHECK();
+    URSM_CUDA(cudaMemcpy(h_out + (size_t)r * s->N, stage.p, m * sizeof(double),
+                         cudaMemcpyDeviceToHost));
+  }
+  URSM_API_END
+}
+
+int ursm_sc_inject(ursm_sc* sc, const double* h_w, const int64_t* h_S, const double* h_kappa,
+                   const double* h_tau, int32_t sample, int32_t reset, double* d_stats,
+                   void* stream) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && h_w && h_S && h_kappa && h_tau && d_stats && sample >= 1,
+               "ursm_sc_inject: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t LN = (size_t)s->L * s->N;
+  if (reset) {
+    URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_sc_stats_len(sc) * sizeof(double), st));
+    s->cnt.zero(st);
+    s->cellmom.zero(st);
+  }
+  s->sample = sample;
+  DevBuf<double> w, kt;
+  DevBuf<unsigned char> S;
+  w.alloc(LN);
+  S.alloc(LN);
+  kt.alloc(2 * (size_t)s->L);
+  std::vector<unsigned char> S8(LN);
+  for (size_t i = 0; i < LN; ++i) S8[i] = h_S[i] != 0;
+  URSM_CUDA(cudaMemcpyAsync(w.p, h_w, LN * sizeof(double), cudaMemcpyHostToDevice, st));
+  URSM_CUDA(cudaMemcpyAsync(S.p, S8.data(), LN, cudaMemcpyHostToDevice, st));
+  URSM_CUDA(cudaMemcpyAsync(kt.p, h_kappa, s->L * sizeof(double), cudaMemcpyHostToDevice, st));
+  URSM_CUDA(cudaMemcpyAsync(kt.p + s->L, h_tau, s->L * sizeof(double), cudaMemcpyHostToDevice, st));
+  sc_inject_kernel<<<(unsigned)s->L, 256, 0, st>>>(w.p, S.p, kt.p, kt.p + s->L, s->G.p, s->L, s->N,
+                                                   s->K, 1.0 / sample, s->cnt.p, s->cellmom.p,
+                                                   d_stats);
+  URSM_LAUNCH_CHECK();
+  URSM_CUDA(cudaStreamSynchronize(st));
+  URSM_API_END
+}
+
+int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kappa_in,
+                        const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t sweep,
+                        float* h_w_out, uint8_t* h_S_out, double* h_kappa_out, double* h_tau_out,
+                        int32_t* h_scan_rounds) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && h_S_in && h_kappa_in && h_tau_in, "ursm_sc_sweep_debug: bad argument");
+  URSM_REQUIRE(s->has_params, "ursm_sc_sweep_debug: call ursm_sc_set_params first");
+  const size_t LN = (size_t)s->L * s->N, L = s->L;
+  DevBuf<unsigned char> S0, Sout;
+  DevBuf<double> kt0, ktout, stats;
+  DevBuf<float> wout;
+  DevBuf<int> rounds;
+  S0.alloc(LN);
+  Sout.alloc(LN);
+  wout.alloc(LN);
+  kt0.alloc(2 * L);
+  ktout.alloc(2 * L);
+  rounds.alloc(L);
+  stats.alloc((size_t)ursm_sc_stats_len(sc));
+  stats.zero();
+  std::vector<unsigned char> S8(LN);
+  for (size_t i = 0; i < LN; ++i) S8[i] = h_S_in[i] != 0;
+  URSM_CUDA(cudaMemcpy(S0.p, S8.data(), LN, cudaMemcpyHostToDevice));
+  URSM_CUDA(cudaMemcpy(kt0.p, h_kappa_in, L * sizeof(double), cudaMemcpyHostToDevice));
+  URSM_CUDA(cudaMemcpy(kt0.p + L, h_tau_in, L * sizeof(double), cudaMemcpyHostToDevice));
+  ScGibbsArgs a;
+  memset(&a, 0, sizeof a);
+  a.burnin = sweep;  // the single sweep counts as retained
+  a.nsweeps = 1;
+  a.thin = 1;
+  a.sample = 1;
+  a.sweep0 = sweep;
+  a.key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1);
+  a.stats = stats.p;
+  a.S0 = S0.p;
+  a.kt0 = kt0.p;
+  a.w_out = wout.p;
+  a.S_out = Sout.p;
+  a.kt_out = ktout.p;
+  a.rounds_out = rounds.p;
+  s->sample = 1;
+  sc_launch(s, a, 0);
+  URSM_CUDA(cudaDeviceSynchronize());
+  if (h_w_out) URSM_CUDA(cudaMemcpy(h_w_out, wout.p, LN * sizeof(float), cudaMemcpyDeviceToHost));
+  if (h_S_out) URSM_CUDA(cudaMemcpy(h_S_out, Sout.p, LN, cudaMemcpyDeviceToHost));
+  if (h_kappa_out)
+    URSM_CUDA(cudaMemcpy(h_kappa_out, ktout.p, L * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h_tau_out)
+    URSM_CUDA(cudaMemcpy(h_tau_out, ktout.p + L, L * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h_scan_rounds)
+    URSM_CUDA(cudaMemcpy(h_scan_rounds, rounds.p, L * sizeof(int), cudaMemcpyDeviceToHost));
+  URSM_API_END
+}
+
+}  // extern "C"

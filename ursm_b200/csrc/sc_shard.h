@@ -1,0 +1,46 @@
+// Device-resident state of one single-cell shard (LogitNormalGibbs_SC's data and
+// chain outputs), shared between sc_gibbs.cu and mle.cu.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace ursm {
+
+struct ScShard {
+  long long L = 0;
+  int N = 0, K = 0;
+  long long cell_offset = 0;
+  DevBuf<float> Yown;            // owned copy of the counts (fp32), or empty
+  const float* Y = nullptr;      // [L][N] counts (owned or borrowed)
+  DevBuf<int> G, order;          // types; local cell ids sorted by type
+  DevBuf<double> R;              // read depth per cell
+  DevBuf<unsigned short> cnt;    // [L][N] number of retained sweeps with S = 1
+  DevBuf<double> cellmom;        // [4][L] E kappa, E tau, E kappa^2, E tau^2
+  DevBuf<int> counter;           // work counter of the persistent kernel
+  DevBuf<double> A;              // [N][K] fp64 parameters (row-major, as given)
+  DevBuf<float> Aslot;           // [K][slots] fp32, slot order of the Gibbs kernel
+  DevBuf<float> scratch;         // [grid][2][slots] CTA-private accumulators (L2-resident)
+  int T = 0, g = 0, slots = 0, smem = 0, occ = 0, grid = 0, num_sms = 0;
+  bool acc_smem = false, has_params = false;
+  double pkappa[2] = {0, 1}, ptau[2] = {0, 1};
+  int sample = 1;                // divisor that turns cnt into E[S]
+  std::vector<long long> type_count, type_start;  // cells per type; offsets into `order`
+};
+
+struct BkShard {
+  long long M = 0;
+  int N = 0, K = 0;
+  long long sample_offset = 0;
+  DevBuf<float> Xown;
+  const float* X = nullptr;      // [M][N] counts
+  DevBuf<double> A;              // [K][N] type-major fp64
+  DevBuf<double> alpha;          // [K]
+  DevBuf<double> W;              // [M][K] (sample-major)
+  DevBuf<double> nA, nB;         // [M][K] sum_i Z_jik: previous / being built
+  DevBuf<double> acc;            // [M][K] scratch (nmf numerators)
+  DevBuf<double> eZjk, eLogW, eW;  // [M][K] each
+  bool has_params = false, has_state = false;
+  int num_sms = 0;
+};
+
+}  // namespace ursm

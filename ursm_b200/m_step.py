@@ -1,0 +1,277 @@
+"""M-step with the reference's class contract (m_step.py:13-320) on the device.
+
+`LogitNormalMLE` keeps the reference constructor and the methods `gem.py` calls
+(`update_suff_stats`, `compute_elbo`, `opt_kappa_tau`, `opt_alpha`, `opt_A_u`)
+and attributes (`A`, `alpha`, `pkappa`, `ptau`).  The O(L*N) work (opt_u,
+update_gd_coeffConst, the E[S]-weighted column sums) and the projected-gradient
+loop for A run in csrc/mle.cu; the K-vector problems (`opt_alpha`,
+`opt_kappa_tau`) stay on the host exactly as SURVEY 8a/a19-a20 scopes them.
+
+The statistics must come from this package's samplers (their `suff_stats` carry
+hidden handles to the device-resident counters); that is what `gem.py` passes.
+"""
+import ctypes
+import logging
+
+import numpy as np
+from scipy.special import gammaln, psi
+
+from . import _lib, dist
+
+
+class LogitNormalMLE(object):
+
+    def __init__(self, BKexpr=None, SCexpr=None, G=None, K=3, itype=None,
+                 hasBK=True, hasSC=True, init_A=None, init_alpha=None,
+                 init_pkappa=None, init_ptau=None, min_A=1e-6, min_alpha=1,
+                 MLE_CONV=1e-4, MLE_maxiter=100,
+                 L_total=None, M_total=None, type_counts=None, N=None):
+        _lib.require_cuda()
+        (self.K, self.min_A, self.min_alpha) = (K, min_A, min_alpha)
+        (self.MLE_CONV, self.MLE_maxiter) = (MLE_CONV, MLE_maxiter)
+        (self.SCexpr, self.G, self.BKexpr) = (SCexpr, G, BKexpr)
+        (self.hasBK, self.hasSC, self.itype) = (hasBK, hasSC, itype)
+        # global sizes (a rank may hold only a shard of the cells / samples)
+        if self.hasSC:
+            self.L = int(L_total if L_total is not None else SCexpr.shape[0])
+            self.N = int(N if N is not None else SCexpr.shape[1])
+            if type_counts is None:
+                type_counts = dist.all_reduce_np(
+                    np.array([len(itype[k]) for k in range(K)], dtype=float))
+            self.type_counts = np.asarray(type_counts).astype(np.int64)
+        if self.hasBK:
+            self.M = int(M_total if M_total is not None else BKexpr.shape[0])
+            self.N = int(N if N is not None else BKexpr.shape[1])
+        self.A = np.copy(init_A)
+        self.alpha = np.copy(init_alpha)
+        self.pkappa = np.copy(init_pkappa)
+        self.ptau = np.copy(init_ptau)
+        self._h = None
+        self.niter_A = np.zeros(K, dtype=int)
+        self.nhalvings = 0
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().ursm_mle_destroy(h)
+            except Exception:
+                pass
+
+    # -- device workspace -------------------------------------------------
+    def _ensure_workspace(self, sc, bk):
+        import torch
+        if self._h is not None and self._owners == (sc, bk):
+            return
+        if self._h is not None:
+            _lib.call("ursm_mle_destroy", self._h)
+        h = ctypes.c_void_p()
+        _lib.call("ursm_mle_create", ctypes.byref(h), sc._h if sc is not None else None,
+                  bk._h if bk is not None else None, self.N, self.K, float(self.min_A))
+        self._h, self._owners = h, (sc, bk)
+        KN = self.K * self.N
+        f = dict(dtype=torch.float64, device="cuda")
+        self._part_local = torch.zeros(KN + self.K, **f)   # per-pass local partials
+        self._part = torch.zeros(KN + self.K, **f)         # all-reduced, per-column current
+        self._cAinv = torch.zeros(KN, **f)
+        self._cA = torch.zeros(KN, **f)
+        self._coeffA = torch.zeros(KN, **f)
+        self._zik = torch.zeros(KN, **f)
+        _lib.call("ursm_mle_set_coeffs", self._h, self._p(self._cAinv), self._p(self._cA),
+                  self._p(self._coeffA))
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _push_A(self):
+        A = _lib.f64(self.A)
+        _lib.call("ursm_mle_set_A", self._h, _lib.ptr(A))
+
+    def _pull_A(self):
+        A = np.empty((self.N, self.K))
+        _lib.call("ursm_mle_get_A", self._h, _lib.ptr(A))
+        self.A = A
+
+    def _pass_u(self, active):
+        """opt_u (:108-115) + update_gd_coeffConst (:118-125) for the active columns."""
+        import torch
+        act = np.ascontiguousarray(active, dtype=np.int32)
+        _lib.call("ursm_mle_pass_u", self._h, _lib.ptr(act), self._p(self._part_local),
+                  _lib.stream_ptr())
+        dist.all_reduce_(self._part_local)  # N*K + K values per outer iteration
+        KN, K, N = self.K * self.N, self.K, self.N
+        idx = torch.as_tensor(np.nonzero(act)[0], device="cuda")
+        if idx.numel():
+            self._part[:KN].view(K, N)[idx] = self._part_local[:KN].view(K, N)[idx]
+        # sum_l R_l log u_l is recomputed for every type on each pass
+        self._part[KN:] = self._part_local[KN:]
+
+    # -- reference API ------------------------------------------------------
+    def update_suff_stats(self, suff_stats):
+        """m_step.py:50-89."""
+        import torch
+        self.suff_stats = suff_stats
+        sc = suff_stats.get("_ursm_sc") if self.hasSC else None
+        bk = suff_stats.get("_ursm_bk") if self.hasBK else None
+        if (self.hasSC and sc is None) or (self.hasBK and bk is None):
+            raise _lib.UrsmError(
+                "LogitNormalMLE.update_suff_stats needs the suff_stats dict produced by "
+                "ursm_b200.e_step_gibbs samplers (device-resident E[S] counters); "
+                "there is no host fallback")
+        self._ensure_workspace(sc, bk)
+        K, N, KN = self.K, self.N, self.K * self.N
+        self._push_A()
+        self.elbo_const = 0
+        self._cAinv.zero_()
+        self._cA.zero_()
+        self._coeffA.zero_()
+        if self.hasBK:
+            tail = suff_stats["_ursm_bk_tail"]
+            self.elbo_const += float(tail[K])
+            self._zik.copy_(bk._stats[:KN])
+            self._cAinv += self._zik
+            self.suff_stats["exp_mean_logW"] = np.asarray(tail[:K]) / float(self.M)
+        if self.hasSC:
+            self.elbo_const += suff_stats["exp_elbo_const"]
+            self._sums = np.asarray(suff_stats["_ursm_sc_sums"], dtype=float)
+            self._coeffA.copy_(sc._stats[:KN])
+            self._cA.copy_(sc._stats[KN:2 * KN])
+            self._cA *= 2.0
+            # sum_{l in k} Y_li E[S_li]
+            _lib.call("ursm_mle_begin", self._h, self._p(self._part_local), _lib.stream_ptr())
+            dist.all_reduce_(self._part_local)
+            self._cAinv += self._part_local[:KN]
+            self._has_cells = self.type_counts > 0
+            self._pass_u(self._has_cells)
+        self._refresh_host_coeffs()
+
+    def _refresh_host_coeffs(self):
+        """Host mirrors of the reference's attributes (N x K), for inspection/tests."""
+        K, N, KN = self.K, self.N, self.K * self.N
+        t = lambda x: np.ascontiguousarray(x.cpu().numpy().reshape(K, N).T)
+        self.gd_coeffAinv = t(self._cAinv)
+        self.gd_coeffA = t(self._cA)
+        if self.hasSC:
+            self.gd_coeffConst = t(self._coeffA - self._part[:KN])
+            u = np.empty(self._owners[0].L)
+            _lib.call("ursm_mle_get_u", self._h, _lib.ptr(u))
+            self.u = u
+        else:
+            self.gd_coeffConst = np.zeros((N, K))
+
+    def opt_kappa_tau(self):
+        """m_step.py:92-103 (closed form; global sums came through the all-reduce)."""
+        sk, skk, st, stt = self._sums
+        km, tm = sk / self.L, st / self.L
+        self.pkappa = np.array([km, skk / self.L - km ** 2])
+        self.ptau = np.array([tm, stt / self.L - tm ** 2])
+
+    def opt_u(self):
+        """m_step.py:108-115 (all types)."""
+        self._push_A()
+        self._pass_u(self._has_cells)
+        self._refresh_host_coeffs()
+
+    def opt_A_u(self):
+        """m_step.py:128-154: every column with cells runs opt_Ak (:157-182)
+        concurrently (columns are independent); the others use the closed form."""
+        if self.hasBK and self.hasSC:
+            init_step = 0.01 / (self.L + self.M)
+        elif self.hasBK:
+            init_step = 0.01 / self.M
+        else:
+            init_step = 0.01 / self.L
+        K = self.K
+        self._push_A()
+        active = np.zeros(K, dtype=np.int32)
+        for k in range(K):
+            if self.hasSC and self.type_counts[k] > 0:
+                active[k] = 1
+            else:
+                _lib.call("ursm_mle_closed_form", self._h, k, self._p(self._zik),
+                          _lib.stream_ptr())
+                logging.debug("\t\tOptimized A%d with closed form solution", k)
+        self.niter_A[:] = 0
+        delta = np.zeros(K)
+        halv = np.zeros(K, dtype=np.int32)
+        while active.any():
+            _lib.call("ursm_mle_step_A", self._h, _lib.ptr(active), self._p(self._part),
+                      float(init_step), _lib.ptr(delta), _lib.ptr(halv), _lib.stream_ptr())
+            self._pass_u(active)
+            self.nhalvings += int(halv[active > 0].sum())
+            for k in np.nonzero(active)[0]:
+                self.niter_A[k] += 1
+                if not (delta[k] > self.MLE_CONV and self.niter_A[k] < self.MLE_maxiter):
+                    active[k] = 0
+                    logging.debug("\t\tOptimized A%d in %d iterations", k, self.niter_A[k])
+        self._pull_A()
+        self._refresh_host_coeffs()
+
+    def opt_alpha(self):
+        """m_step.py:185-206: backtracking gradient descent on the K-vector (host)."""
+        (converged, niter) = (self.MLE_CONV + 1, 0)
+        while (converged > self.MLE_CONV) and (niter < self.MLE_maxiter):
+            old_alpha = np.copy(self.alpha)
+            self.alpha = self.backtracking(
+                old_val=old_alpha, grad_func=lambda a: (-self.get_grad_alpha(a)),
+                obj_func=lambda a: (-self.get_obj_alpha(a)), init_step=10)[0]
+            self.alpha = np.maximum(self.min_alpha, self.alpha)
+            niter += 1
+            converged = np.linalg.norm(self.alpha - old_alpha)
+        logging.debug("\t\tOptimized alpha in %s iterations", niter)
+        return niter
+
+    def backtracking(self, old_val, grad_func, obj_func, init_step=0.1, proj_func=None):
+        """m_step.py:209-233 (host version, used for alpha only)."""
+        grad_old, obj_old = grad_func(old_val), obj_func(old_val)
+        stepsize = init_step
+
+        def trial(s):
+            v = old_val - s * grad_old
+            return proj_func(v) if proj_func is not None else v
+
+        new_val = trial(stepsize)
+        Gt = (old_val - new_val) / stepsize
+        obj_new = obj_func(new_val)
+        while obj_new > (obj_old + (stepsize * 0.5) * (Gt ** 2).sum()
+                         - stepsize * np.dot(grad_old, Gt)):
+            stepsize = stepsize * 0.5
+            new_val = trial(stepsize)
+            Gt = (old_val - new_val) / stepsize
+            obj_new = obj_func(new_val)
+        return (new_val, obj_new, stepsize)
+
+    def get_grad_alpha(self, alpha_val):
+        """m_step.py:236-241."""
+        return self.suff_stats["exp_mean_logW"] + psi(sum(alpha_val)) - psi(alpha_val)
+
+    def get_obj_alpha(self, alpha_val):
+        """m_step.py:244-251 (scaled by 1/M)."""
+        obj = np.dot(self.suff_stats["exp_mean_logW"], alpha_val)
+        obj += gammaln(sum(alpha_val)) - sum(gammaln(alpha_val))
+        return obj
+
+    def compute_elbo(self):
+        """m_step.py:290-320 (scaled by 1/N)."""
+        KN = self.K * self.N
+        terms = np.zeros(3)
+        self._push_A()
+        _lib.call("ursm_mle_elbo_terms", self._h,
+                  self._p(self._part) if self.hasSC else None, _lib.ptr(terms),
+                  _lib.stream_ptr())
+        elbo = self.elbo_const
+        elbo += terms[0]
+        if self.hasBK:
+            elbo += self.get_obj_alpha(self.alpha) * self.M
+        if self.hasSC:
+            elbo += terms[1]
+            elbo += terms[2]
+            elbo -= float(self._part[KN:].sum().item())
+            sk, skk, st, stt = self._sums
+            elbo -= np.log(self.pkappa[1] * self.ptau[1]) * self.L / 2.0
+            elbo -= (skk - 2 * self.pkappa[0] * sk + self.L * (self.pkappa[0] ** 2)) \
+                / (2.0 * self.pkappa[1])
+            elbo -= (stt - 2 * self.ptau[0] * st + self.L * (self.ptau[0] ** 2)) \
+                / (2.0 * self.ptau[1])
+        return elbo / self.N

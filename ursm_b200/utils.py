@@ -1,0 +1,23 @@
+"""Helper functions with the reference's names (utils.py:8-38)."""
+import numpy as np
+
+from . import _lib
+
+
+def simplex_proj(y, min_y):
+    """Project `y` onto {y >= min_y, sum(y) = 1}  (utils.py:8-31).
+
+    Runs the same sort-free device routine the M-step kernel uses
+    (csrc/mle.cu::proj_lambda); the projection is unique, so the result equals
+    the reference's sort-based one up to summation-order rounding.
+    """
+    _lib.require_cuda()
+    y = _lib.f64(np.asarray(y).ravel())
+    out = np.empty_like(y)
+    _lib.call("ursm_simplex_proj", _lib.ptr(y), int(y.size), float(min_y), _lib.ptr(out))
+    return out
+
+
+def std_row(B):
+    """Rows scaled to sum to one (utils.py:34-38)."""
+    return np.true_divide(B, B.sum(axis=1)[:, np.newaxis])
