@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Benchmark of the URSM Monte-Carlo EM hot path on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+
+A *step* is one EM iteration (gem.py:163-192): the single-cell Gibbs E-step
+(burnin + sample sweeps of draw_w / draw_S / draw_kappa_tau), the bulk Gibbs E-step
+(draw_W / draw_Z, `-no_mean_approx`), update_suff_stats, the ELBO twice and the
+M-step (opt_kappa_tau, opt_alpha, opt_A_u).  Work is counted in Gibbs cell x gene
+updates: (L*N + M*N) * (burnin + sample*thin) per step.
+
+  value     updates of all ranks / device time of the K timed steps, inputs resident in
+            HBM (weak scaling: every rank holds one copy of the workload's rows)
+  e2e       the same metric through the public API from HOST buffers: every step
+            uploads the count matrices (pinned host memory), runs the EM iteration and
+            reads A / alpha / pkappa / ptau / E[kappa] / E[tau] / E[W] / E[S] back
+  roofline  the single-cell Gibbs kernel against the measured HBM peak, using the
+            algorithmic bytes per update of SURVEY 8d / DESIGN.md
+  cpu_baseline   the CPU oracle (numpy restatement of the reference + compiled PG
+            sampler) on a bounded row-subsample of the same workload, on this box's cores
+
+`--impl reference` prints the CPU arm alone (rank 0 only under torchrun).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# per-GPU row counts of BASELINE.json's configs (weak scaling: each rank holds these)
+WORKLOADS = {
+    # configs[1]: the configuration the metric is quoted on for one GPU
+    "c2": dict(K=5, L=2000, M=200, N=5000, burnin=50, sample=50, desc="synthetic joint fit K=5, "
+               "2,000 cells, 200 bulk samples, 5,000 genes per GPU"),
+    # configs[2] / 8: the per-GPU share of the 8-GPU target problem
+    "c3": dict(K=10, L=12500, M=125, N=20000, burnin=50, sample=100, desc="1/8 of the K=10, "
+               "100,000-cell x 1,000-bulk x 20,000-gene joint fit per GPU"),
+    "c4": dict(K=10, L=0, M=2500, N=20000, burnin=50, sample=100, desc="bulk-only K=10, 2,500 "
+               "bulk samples x 20,000 genes per GPU (1/8 of configs[3])"),
+    "c5": dict(K=20, L=125000, M=0, N=2000, burnin=50, sample=100, desc="single-cell-only K=20, "
+               "125,000 cells x 2,000 genes per GPU (1/8 of configs[4])"),
+    "tiny": dict(K=3, L=64, M=16, N=400, burnin=5, sample=5, desc="tiny self-test"),
+}
+METRIC = "gibbs_cell_gene_updates_per_s"
+UNIT = "updates/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def updates_per_step(cfg):
+    return (cfg["L"] * cfg["N"] + cfg["M"] * cfg["N"]) * (cfg["burnin"] + cfg["sample"])
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle on a bounded row-subsample (the only place bench.py runs oracle/)
+# ---------------------------------------------------------------------------
+def cpu_sample_sizes(cfg):
+    K = cfg["K"]
+    Ls = min(cfg["L"], max(2 * K, 8)) if cfg["L"] else 0
+    Ms = min(cfg["M"], 4) if cfg["M"] else 0
+    # keep one step to a few seconds: ~3 us per single-cell entry, ~5 us per bulk entry
+    per_sweep = 3e-6 * Ls * cfg["N"] + 5e-6 * Ms * cfg["N"]
+    sweeps = int(max(2, min(cfg["burnin"] + cfg["sample"], 6.0 / max(per_sweep, 1e-9))))
+    burn = sweeps // 2
+    return Ls, Ms, burn, sweeps - burn
+
+
+def run_cpu_arm(cfg, steps, warmup, seed=0, verbose=False):
+    """Times the oracle (kind "port": the reference is pure Python and cannot travel to
+    the GPU box; its one native dependency, pypolyagamma, is restated in C/OpenMP)."""
+    from oracle import ursm_oracle as orc
+    K, N = cfg["K"], cfg["N"]
+    Ls, Ms, burn, samp = cpu_sample_sizes(cfg)
+    cores = max(1, min(os.cpu_count() or 1, orc.pg_c_max_threads()))
+    sim = orc.simulate(N=N, K=K, L=Ls, M=Ms, seed=seed)
+    Y, X, G = sim.get("Y"), sim.get("X"), sim.get("G")
+    rng = np.random.RandomState(seed + 1)
+    gem = orc.OracleGEM(BKexpr=X, SCexpr=Y, K=K, G=G, burnin=burn, sample=samp, thin=1,
+                        bk_mean_approx=False, MLE_CONV=1e-6, MLE_maxiter=500, EM_CONV=1e-6,
+                        EM_maxiter=1, rng=rng, pg_factory=orc.CPGSampler, pg_draw=orc.pgdrawv_c)
+    # build the samplers exactly as OracleGEM.gem() does, with `cores` PG generators
+    if gem.hasSC:
+        gem.sc = orc.OracleGibbsSC(gem.init_A, gem.init_pkappa, gem.init_ptau, Y, G, gem.itype,
+                                   rng=rng, num_threads=cores, pg_factory=orc.CPGSampler,
+                                   pg_draw=orc.pgdrawv_c)
+        gem.sc.init_gibbs()
+    if gem.hasBK:
+        gem.bk = orc.OracleGibbsBK(gem.init_A, gem.init_alpha, X, None, rng=rng)
+        gem.bk.init_gibbs()
+    gem.mle = orc.OracleMLE(X, Y, G, K, gem.itype, gem.hasBK, gem.hasSC, gem.init_A,
+                            gem.init_alpha, gem.init_pkappa, gem.init_ptau, 1e-6, 1, 1e-6, 500)
+    upd = (Ls * N + Ms * N) * (burn + samp)
+    e_times, m_times = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        gem.estep()
+        t1 = time.perf_counter()
+        gem.mle.update_suff_stats(gem.suff_stats)
+        gem.mle.compute_elbo()
+        if gem.hasSC:
+            gem.mle.opt_kappa_tau()
+            gem.pkappa, gem.ptau = gem.mle.pkappa, gem.mle.ptau
+        if gem.hasBK:
+            gem.mle.opt_alpha()
+            gem.alpha = gem.mle.alpha
+        gem.mle.opt_A_u()
+        gem.A = gem.mle.A
+        gem.mle.compute_elbo()
+        t2 = time.perf_counter()
+        if it >= warmup:
+            e_times.append(t1 - t0)
+            m_times.append(t2 - t1)
+        if verbose:
+            print("cpu step %d: E %.2fs M %.2fs" % (it, t1 - t0, t2 - t1), file=sys.stderr)
+    e_mean, m_mean = float(np.mean(e_times)), float(np.mean(m_times))
+    sample = ("row-subsample of the workload at the full gene count: %d cells + %d bulk samples x "
+              "%d genes, K=%d, burnin %d / sample %d sweeps per step; value = Gibbs updates / "
+              "E-step seconds (M-step of the subsample timed separately: %.2f s)"
+              % (Ls, Ms, N, K, burn, samp, m_mean))
+    return dict(value=upd / e_mean, unit=UNIT, cores=cores, kind="port", sample=sample,
+                estep_s=e_mean, mstep_s=m_mean, updates_per_step=upd)
+
+
+def reference_main(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    res = run_cpu_arm(cfg, args.steps, args.warmup, verbose=args.verbose)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (res["estep_s"] + res["mstep_s"]), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + cfg["desc"], "K": cfg["K"], "N": cfg["N"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def gpu_main(args, cfg):
+    import torch
+    import torch.distributed as td
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sm_100a path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    from ursm_b200 import _lib, synth
+    from ursm_b200.gem import LogitNormalGEM
+    lib = _lib.load()
+
+    K, N, Ll, Ml = cfg["K"], cfg["N"], cfg["L"], cfg["M"]
+    burnin, sample = cfg["burnin"], cfg["sample"]
+    seed = 0
+    A_true = synth.profile_matrix(N, K, seed=seed)
+    dev_SC = dev_BK = G = None
+    if Ll:
+        G = (np.arange(rank * Ll, (rank + 1) * Ll) % K).astype(np.int64)
+        dev_SC = synth.cells_on_device(A_true, G, seed, row_offset=rank * Ll)[0]
+    if Ml:
+        dev_BK = synth.bulk_on_device(A_true, Ml, seed, row_offset=rank * Ml)[0]
+
+    def make_gem(**kw):
+        return LogitNormalGEM(K=K, G=G, burnin=burnin, sample=sample, thin=1,
+                              bk_mean_approx=False, MLE_CONV=1e-6, MLE_maxiter=args.mle_maxiter,
+                              EM_CONV=1e-6, EM_maxiter=10 ** 6, seed=1, **kw)
+
+    gem = make_gem(device_SC=dev_SC, device_BK=dev_BK, L_total=Ll * world, M_total=Ml * world,
+                   row_offset_SC=rank * Ll, row_offset_BK=rank * Ml)
+    gem.init_gibbs()
+    gem.init_mle()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB of L2
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        flush.zero_()  # L2 flush between iterations (inputs at c2 are smaller than L2)
+        return gem.em_iteration()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.ursm_launch_count_reset()
+    sc_ms, bk_ms, e_ms = [], [], []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    t_wall = time.perf_counter()
+    ev[0].record()
+    elbo = None
+    for _ in range(args.steps):
+        _, elbo = one_step()
+        if gem.hasSC:
+            sc_ms.append(gem.Gibbs_SC.kernel_ms())
+        if gem.hasBK:
+            bk_ms.append(gem.Gibbs_BK.kernel_ms())
+    ev[1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = int(lib.ursm_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = ev[0].elapsed_time(ev[1])
+    t = torch.tensor([dev_ms, t_wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    upd_rank = updates_per_step(cfg)
+    value = upd_rank * world * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers -> public API -> host results, every step -------------
+    e2e = None
+    if not args.no_e2e:
+        hY = hX = None
+        if Ll:
+            hY = torch.empty(Ll, N, dtype=torch.float64).pin_memory()
+            hY.copy_(dev_SC)
+        if Ml:
+            hX = torch.empty(Ml, N, dtype=torch.float64).pin_memory()
+            hX.copy_(dev_BK)
+        nY = hY.numpy() if hY is not None else None
+        nX = hX.numpy() if hX is not None else None
+        h2d = (nY.nbytes if nY is not None else 0) + (nX.nbytes if nX is not None else 0)
+        init_A = np.copy(gem.init_A)
+        d2h_box = [0]
+
+        def e2e_step():
+            flush.zero_()
+            # host arrays are this rank's rows: single-process semantics per rank plus the
+            # all-reduce inside the samplers (weak scaling, as in the device-resident arm)
+            g2 = make_gem(SCexpr=nY, BKexpr=nX, init_A=init_A) if world == 1 else None
+            if g2 is None:
+                raise SystemExit("e2e arm is run at N=1 only")
+            g2.init_gibbs()
+            g2.init_mle()
+            g2.em_iteration()
+            out = [g2.A, g2.alpha if g2.hasBK else None]
+            st = g2.gathered_stats()
+            d2h_box[0] = sum(np.asarray(v).nbytes for v in st.values()) + g2.A.nbytes
+            return out, st
+
+        if world == 1:
+            for _ in range(min(args.warmup, 2)):
+                e2e_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_e2e = max(1, min(args.steps, 3))
+            for _ in range(n_e2e):
+                e2e_step()
+            torch.cuda.synchronize()
+            e2e_s = (time.perf_counter() - t0) / n_e2e
+            e2e = {"value": upd_rank / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h_box[0]), "ms_per_step": 1e3 * e2e_s,
+                   "steps": n_e2e}
+        else:
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "e2e arm measured at N=1"}
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return 0
+
+    peak, peak_src = load_peaks()
+    roofline = None
+    sweeps = burnin + sample
+    if sc_ms:
+        b_per_update = (2.0 * burnin + 6.0 * sample) / sweeps  # SURVEY 8d / DESIGN.md
+        alg_bytes = b_per_update * Ll * N * sweeps
+        k_ms = float(np.mean(sc_ms))
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "sc_gibbs_kernel", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "kernel_ms": k_ms,
+                    "bytes_per_update": b_per_update,
+                    "updates_per_s_kernel": Ll * N * sweeps / (k_ms * 1e-3)}
+    elif bk_ms:
+        alg_bytes = 4.0 * Ml * N * sweeps
+        k_ms = float(np.mean(bk_ms))
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "bk_tile_kernel<2> (all sweeps)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                    "bytes_per_update": 4.0}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        r = run_cpu_arm(cfg, steps=1, warmup=0, verbose=args.verbose)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 sampler / f64 reductions",
+        "data": "synthetic (demo_simulate_data.py distributions, generated on device)",
+        "config": {"workload": args.workload + ": " + cfg["desc"], "K": K, "N": N,
+                   "cells_per_gpu": Ll, "bulk_per_gpu": Ml, "burnin": burnin, "sample": sample,
+                   "thin": 1, "bulk_mode": "gibbs (-no_mean_approx)",
+                   "MLE_maxiter": args.mle_maxiter, "l2": "flushed between steps (256 MiB write)",
+                   "parallelism": "cells/bulk samples sharded over %d rank(s)" % world},
+        "s_per_em_iter": dev_ms / args.steps / 1e3, "wall_ms_per_step": wall_ms / args.steps,
+        "kernel_ms": {"sc_gibbs": float(np.mean(sc_ms)) if sc_ms else None,
+                      "bk_estep": float(np.mean(bk_ms)) if bk_ms else None},
+        "elbo_last": elbo, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ursm_b200", choices=["ursm_b200", "reference"])
+    ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mle-maxiter", dest="mle_maxiter", type=int, default=500)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return reference_main(args, cfg)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            # not launched by torchrun: re-launch ourselves one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                   "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+                   "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)]
+            cmd += sys.argv[1:]
+            return subprocess.call(cmd)
+    return gpu_main(args, cfg)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

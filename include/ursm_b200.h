@@ -85,6 +85,8 @@ int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kapp
                         const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t sweep,
                         float* h_w_out, uint8_t* h_S_out, double* h_kappa_out,
                         double* h_tau_out, int32_t* h_scan_rounds);
+/* device time (ms, CUDA events on the launch stream) of the last Gibbs kernel */
+int ursm_sc_kernel_ms(ursm_sc* sc, float* ms);
 /* launch geometry the shard picked (threads per CTA, genes per thread, CTAs) */
 int ursm_sc_geometry(const ursm_sc* sc, int32_t* threads, int32_t* genes_per_thread,
                      int32_t* grid, int32_t* smem_bytes, int32_t* acc_in_smem);
@@ -117,6 +119,8 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
 int ursm_bk_get_sample_stats(ursm_bk* bk, double* h_exp_Zjk, double* h_exp_logW,
                              double* h_exp_W);
 int ursm_bk_get_W(ursm_bk* bk, double* h_W);
+/* device time (ms) of the last bulk E-step's kernels (mean step or all Gibbs sweeps) */
+int ursm_bk_kernel_ms(ursm_bk* bk, float* ms);
 
 /* ---- M-step: m_step.py:13-320 ------------------------------------------------
  * The workspace borrows the shards (it reads Y, the E[S] counters, read depths).

@@ -196,6 +196,69 @@ def pgdrawv(samplers, ns, zs, out):
         out[i] = s.draw(zs[i])
 
 
+# ---- C build of the same sampler (oracle/pg_devroye.c, OpenMP) -------------
+# pypolyagamma is C++/OpenMP in the reference's environment; timing the pure-Python
+# restatement above as "the reference's CPU path" would be unfair to it, so the
+# cpu_baseline leg of bench.py uses this compiled restatement through the same
+# `pgdrawvpar`-shaped hook (one generator per OpenMP thread, e_step_gibbs.py:200-209).
+
+_PG_C = None
+
+
+def _pg_c():
+    global _PG_C
+    if _PG_C is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build",
+                            "libpg_devroye.so")
+        if not os.path.exists(path):
+            from . import build as _b
+            _b.build_pg()
+        lib = ctypes.CDLL(path)
+        lib.pg_pool_create.restype = ctypes.c_void_p
+        lib.pg_pool_create.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        lib.pg_pool_destroy.argtypes = [ctypes.c_void_p]
+        lib.pg_drawv.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                 ctypes.c_void_p]
+        lib.pg_mass_texpon.restype = ctypes.c_double
+        lib.pg_mass_texpon.argtypes = [ctypes.c_double]
+        lib.pg_max_threads.restype = ctypes.c_int
+        _PG_C = lib
+    return _PG_C
+
+
+def pg_c_max_threads():
+    return int(_pg_c().pg_max_threads())
+
+
+class CPGSampler(object):
+    """`PyPolyaGamma(seed)` stand-in backed by pg_devroye.c (one per OpenMP thread)."""
+
+    def __init__(self, seed=0):
+        self.seed = int(seed)
+
+
+def pgdrawv_c(samplers, ns, zs, out):
+    """`pgdrawvpar(ppgs, ns, zs, out)` stand-in: len(samplers) OpenMP threads, in place."""
+    import ctypes
+    lib = _pg_c()
+    pool = getattr(samplers[0], "_pool", None)
+    if pool is None:
+        seeds = np.array([s.seed for s in samplers], dtype=np.uint64)
+        pool = lib.pg_pool_create(len(samplers), seeds.ctypes.data_as(ctypes.c_void_p))
+        samplers[0]._pool = pool
+    zs = np.ascontiguousarray(zs, dtype=np.float64)
+    if out.flags["C_CONTIGUOUS"] and out.dtype == np.float64:
+        lib.pg_drawv(pool, zs.size, zs.ctypes.data_as(ctypes.c_void_p),
+                     out.ctypes.data_as(ctypes.c_void_p))
+    else:
+        tmp = np.empty(zs.size)
+        lib.pg_drawv(pool, zs.size, zs.ctypes.data_as(ctypes.c_void_p),
+                     tmp.ctypes.data_as(ctypes.c_void_p))
+        out[:] = tmp
+
+
 # --------------------------------------------------------------------------
 # e_step_gibbs.py:19-164  --  bulk samples
 # --------------------------------------------------------------------------

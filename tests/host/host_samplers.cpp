@@ -43,4 +43,25 @@ void h_uniform(int count, uint64_t seed, double* out) {
   Philox g(seed, 0u, 0u, 0u);
   for (int i = 0; i < count; ++i) out[i] = g.uniform();
 }
+// replay helpers for the GPU parity tests: the uniforms / normals the production
+// single-cell kernel consumes for (cell, sweep), and the float32 threshold
+void h_gene_uniforms(uint64_t key, uint32_t cell, uint32_t sweep, int N, double* out) {
+  for (int i = 0; i < N; ++i) {
+    Philox g(key, (uint32_t)i, cell, kPurposeGene | sweep);
+    out[i] = g.uniform();
+  }
+}
+void h_cell_normals(uint64_t key, uint32_t cell, uint32_t sweep, double* out2) {
+  Philox g(key, 0xffffffffu, cell, kPurposeCell | sweep);
+  normal_pair(g, out2[0], out2[1]);
+}
+void h_init_bits(uint64_t key, uint32_t cell, int N, int* out) {
+  for (int i = 0; i < N; ++i) {
+    Philox g(key, (uint32_t)i, cell, kPurposeInit);
+    out[i] = (int)(g.next() >> 31);
+  }
+}
+uint64_t h_sc_key(uint64_t seed, uint64_t em_iter) {
+  return seed + 0x9E3779B97F4A7C15ull * (em_iter + 1);
+}
 }

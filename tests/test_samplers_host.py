@@ -2,8 +2,6 @@
 (tests/host/host_samplers.cpp includes the very header the kernels inline) and
 checked against exact moments / pmfs.  No GPU needed."""
 import ctypes
-import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -12,28 +10,10 @@ from scipy.special import expit
 
 from oracle import ursm_oracle as orc
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "host", "host_samplers.cpp")
-OUT = os.path.join(HERE, "host", "_build", "libhost_samplers.so")
-HDRS = [os.path.join(HERE, "..", "ursm_b200", "csrc", h) for h in ("samplers.cuh", "rng.cuh")]
-
 
 @pytest.fixture(scope="module")
-def lib():
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    newest = max(os.path.getmtime(p) for p in [SRC] + HDRS)
-    if not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", OUT, SRC])
-    L = ctypes.CDLL(OUT)
-    L.h_pg_mass.restype = ctypes.c_double
-    L.h_pg_mass.argtypes = [ctypes.c_double]
-    L.h_s_threshold.restype = ctypes.c_double
-    L.h_s_threshold.argtypes = [ctypes.c_double] * 4
-    L.h_pg_draws.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]
-    L.h_binomial.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_uint64,
-                             ctypes.c_void_p]
-    L.h_gamma.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]
-    return L
+def lib(hostlib):
+    return hostlib
 
 
 def _dbl(n):

@@ -34,6 +34,8 @@ SIGNATURES = {
     "ursm_sc_inject": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ursm_sc_sweep_debug": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_u64, c_i32, c_vp, c_vp,
                                     c_vp, c_vp, c_vp]),
+    "ursm_sc_kernel_ms": (c_int, [c_vp, c_vp]),
+    "ursm_bk_kernel_ms": (c_int, [c_vp, c_vp]),
     "ursm_sc_geometry": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ursm_bk_create": (c_int, [PP, c_vp, c_i64, c_i32, c_i32, c_i64]),
     "ursm_bk_create_dev": (c_int, [PP, c_vp, c_i64, c_i32, c_i32, c_i64]),

@@ -225,6 +225,18 @@ static void bk_launch_tile(BkShard* b, BkTileArgs& a, cudaStream_t st) {
   URSM_LAUNCH_CHECK();
 }
 
+static void bk_time_begin(BkShard* b, cudaStream_t st) {
+  if (!b->ev0) {
+    URSM_CUDA(cudaEventCreate(&b->ev0));
+    URSM_CUDA(cudaEventCreate(&b->ev1));
+  }
+  URSM_CUDA(cudaEventRecord(b->ev0, st));
+}
+static void bk_time_end(BkShard* b, cudaStream_t st) {
+  URSM_CUDA(cudaEventRecord(b->ev1, st));
+  b->timed = true;
+}
+
 static void bk_finish_create(BkShard* b) {
   int dev;
   URSM_CUDA(cudaGetDevice(&dev));
@@ -309,6 +321,15 @@ int64_t ursm_bk_stats_len(const ursm_bk* bk) {
   return (int64_t)b->N * b->K + b->K + 1;
 }
 
+int ursm_bk_kernel_ms(ursm_bk* bk, float* ms) {
+  URSM_API_BEGIN
+  BkShard* b = reinterpret_cast<BkShard*>(bk);
+  URSM_REQUIRE(b && ms && b->timed, "ursm_bk_kernel_ms: no bulk E-step has been launched");
+  URSM_CUDA(cudaEventSynchronize(b->ev1));
+  URSM_CUDA(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+  URSM_API_END
+}
+
 int ursm_bk_set_params(ursm_bk* bk, const double* h_A, const double* h_alpha) {
   URSM_API_BEGIN
   BkShard* b = reinterpret_cast<BkShard*>(bk);
@@ -348,6 +369,7 @@ int ursm_bk_mean_step(ursm_bk* bk, double* d_stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const size_t MK = (size_t)b->M * b->K;
   const unsigned mb = (unsigned)((b->M + 127) / 128), mkb = (unsigned)((MK + 255) / 256);
+  bk_time_begin(b, st);
   URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_bk_stats_len(bk) * sizeof(double), st));
   b->acc.zero(st);
   b->eZjk.zero(st);
@@ -366,6 +388,7 @@ int ursm_bk_mean_step(ursm_bk* bk, double* d_stats, void* stream) {
   bk_tail_kernel<<<1, 1024, 0, st>>>(b->eZjk.p, b->eLogW.p, b->M, b->K,
                                      d_stats + (size_t)b->N * b->K);
   URSM_LAUNCH_CHECK();
+  bk_time_end(b, st);
   URSM_API_END
 }
 
@@ -380,6 +403,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   const unsigned mb = (unsigned)((b->M + 127) / 128);
   const unsigned long long key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1) + 0x5bd1e995ull;
   const double inv = 1.0 / sample;
+  bk_time_begin(b, st);
   URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_bk_stats_len(bk) * sizeof(double), st));
   b->eZjk.zero(st);
   b->eLogW.zero(st);
@@ -418,6 +442,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   bk_tail_kernel<<<1, 1024, 0, st>>>(b->eZjk.p, b->eLogW.p, b->M, b->K,
                                      d_stats + (size_t)b->N * b->K);
   URSM_LAUNCH_CHECK();
+  bk_time_end(b, st);
   URSM_API_END
 }
 

@@ -535,11 +535,18 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
   a.counter = s->counter.p;
   a.flush_every = 16;
   URSM_CUDA(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
+  if (!s->ev0) {
+    URSM_CUDA(cudaEventCreate(&s->ev0));
+    URSM_CUDA(cudaEventCreate(&s->ev1));
+  }
+  URSM_CUDA(cudaEventRecord(s->ev0, st));
   if (s->acc_smem)
     sc_gibbs_kernel<true><<<s->grid, s->T, s->smem, st>>>(a);
   else
     sc_gibbs_kernel<false><<<s->grid, s->T, s->smem, st>>>(a);
   URSM_LAUNCH_CHECK();
+  URSM_CUDA(cudaEventRecord(s->ev1, st));
+  s->timed = true;
 }
 
 }  // namespace ursm
@@ -612,6 +619,15 @@ int ursm_sc_geometry(const ursm_sc* sc, int32_t* threads, int32_t* genes_per_thr
   if (smem_bytes) *smem_bytes = s->smem;
   if (acc_in_smem) *acc_in_smem = s->acc_smem ? 1 : 0;
   return 0;
+}
+
+int ursm_sc_kernel_ms(ursm_sc* sc, float* ms) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && ms && s->timed, "ursm_sc_kernel_ms: no Gibbs kernel has been launched");
+  URSM_CUDA(cudaEventSynchronize(s->ev1));
+  URSM_CUDA(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+  URSM_API_END
 }
 
 int ursm_sc_set_params(ursm_sc* sc, const double* h_A, const double* h_pkappa,

@@ -25,6 +25,12 @@ struct ScShard {
   double pkappa[2] = {0, 1}, ptau[2] = {0, 1};
   int sample = 1;                // divisor that turns cnt into E[S]
   std::vector<long long> type_count, type_start;  // cells per type; offsets into `order`
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // bracket the last Gibbs kernel launch
+  bool timed = false;
+  ~ScShard() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
 };
 
 struct BkShard {
@@ -41,6 +47,12 @@ struct BkShard {
   DevBuf<double> eZjk, eLogW, eW;  // [M][K] each
   bool has_params = false, has_state = false;
   int num_sms = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // bracket the last E-step's kernels
+  bool timed = false;
+  ~BkShard() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
 };
 
 }  // namespace ursm

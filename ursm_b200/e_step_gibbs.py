@@ -147,6 +147,12 @@ class LogitNormalGibbs_SC(object):
                   _lib.ptr(rounds))
         return w, S_out, k_out, t_out, rounds
 
+    def kernel_ms(self):
+        """Device time of the last Gibbs kernel (CUDA events on its launch stream)."""
+        ms = ctypes.c_float()
+        _lib.call("ursm_sc_kernel_ms", self._h, ctypes.byref(ms))
+        return ms.value
+
     def geometry(self):
         v = [ctypes.c_int32() for _ in range(5)]
         _lib.load().ursm_sc_geometry(self._h, *[ctypes.byref(x) for x in v])
@@ -267,6 +273,12 @@ class LogitNormalGibbs_BK(object):
                       sp, _lib.stream_ptr())
         self.em_iter += 1
         self._publish()
+
+    def kernel_ms(self):
+        """Device time of the last bulk E-step's kernels."""
+        ms = ctypes.c_float()
+        _lib.call("ursm_bk_kernel_ms", self._h, ctypes.byref(ms))
+        return ms.value
 
     def _push_params(self):
         A, al = _lib.f64(self.A), _lib.f64(self.alpha)
