@@ -55,6 +55,8 @@ def hostlib():
                               ctypes.c_void_p)
     L.h_pg_mass.restype = dbl
     L.h_pg_mass.argtypes = [dbl]
+    L.h_ndtri_sq.restype = dbl
+    L.h_ndtri_sq.argtypes = [dbl]
     L.h_s_threshold.restype = dbl
     L.h_s_threshold.argtypes = [dbl] * 4
     L.h_pg_draws.argtypes = [dbl, i32, u64, vp]

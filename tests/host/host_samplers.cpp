@@ -11,11 +11,12 @@ void h_philox(uint64_t key, uint32_t x, uint32_t y, uint32_t z, uint32_t* out, i
   Philox g(key, x, y, z);
   for (int i = 0; i < 4 * nblocks; ++i) out[i] = g.next();
 }
-double h_pg_mass(double z) { return pg_mass_texpon((float)z); }
+double h_pg_mass(double z) { return pg_tilt((float)(2.0 * z)).mass_right; }
+double h_ndtri_sq(double v) { return ndtri_sq((float)v); }
 void h_pg_draws(double psi, int n, uint64_t seed, double* out) {
   for (int i = 0; i < n; ++i) {
     Philox g(seed, (uint32_t)i, 7u, 0u);
-    out[i] = pg1_devroye((float)psi, g);
+    out[i] = pg1_draw((float)psi, g);
   }
 }
 double h_s_threshold(double psi, double u, double a, double R) {
@@ -47,8 +48,9 @@ void h_uniform(int count, uint64_t seed, double* out) {
 // single-cell kernel consumes for (cell, sweep), and the float32 threshold
 void h_gene_uniforms(uint64_t key, uint32_t cell, uint32_t sweep, int N, double* out) {
   for (int i = 0; i < N; ++i) {
-    Philox g(key, (uint32_t)i, cell, kPurposeGene | sweep);
-    out[i] = g.uniform();
+    uint32_t r0, r1, r2, r3;  // the S uniform is word 3 of the gene's first attempt block
+    philox_block(key, (uint32_t)i, cell, kPurposeGene | sweep, 0u, r0, r1, r2, r3);
+    out[i] = u01(r3);
   }
 }
 void h_cell_normals(uint64_t key, uint32_t cell, uint32_t sweep, double* out2) {

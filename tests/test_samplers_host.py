@@ -45,9 +45,28 @@ def test_uniform_open_interval(lib):
     assert stats.kstest(u, "uniform").pvalue > 1e-3
 
 
-def test_pg_mass_matches_oracle(lib):
-    for z in (0.0, 0.1, 0.5, 1.0, 1.5, 1.5624, 1.5626, 2.0, 3.0, 5.0, 8.0, 15.0, 50.0, 500.0):
-        np.testing.assert_allclose(lib.h_pg_mass(z), orc.pg_mass_texpon(z), rtol=5e-6, atol=1e-30)
+def test_pg_mixture_weight_is_the_envelope_mass_ratio(lib):
+    """mass_right = p/(p + q) with p, q the integrals of the envelope pieces the sampler
+    proposes from (samplers.cuh header), integrated numerically here."""
+    from scipy.integrate import quad
+    t = 0.64
+    for z in (0.0, 0.1, 0.5, 1.0, 1.5, 1.5624, 1.5626, 2.0, 3.0, 5.0, 8.0):
+        fz = np.pi ** 2 / 8 + z * z / 2
+        p = quad(lambda x: np.pi / 2 * np.exp(-fz * x), t, np.inf)[0]
+        a0 = lambda x: np.pi / 2 * (2 / (np.pi * x)) ** 1.5 * np.exp(-1 / (2 * x))
+        if z < 1 / t:   # untilted truncated Levy piece
+            q = quad(a0, 0, t)[0]
+        else:           # tilted piece on the whole half line (inverse Gaussian)
+            q = quad(lambda x: a0(x) * np.exp(-z * z * x / 2), 0, np.inf)[0]
+        np.testing.assert_allclose(lib.h_pg_mass(z), p / (p + q), rtol=2e-6)
+    assert lib.h_pg_mass(50.0) == 0.0 and lib.h_pg_mass(500.0) == 0.0
+
+
+def test_ndtri_sq(lib):
+    from scipy.special import ndtri
+    for v in (1e-8, 1e-6, 1e-4, 0.0016, 0.0018, 0.01, 0.1056, 0.3, 0.5 - 1e-3, 0.7, 0.999, 1 - 1e-6):
+        want = ndtri(np.float64(np.float32(v))) ** 2
+        np.testing.assert_allclose(lib.h_ndtri_sq(v), want, rtol=(1e-5 if v < 1e-5 else 3e-6), atol=1e-9)
 
 
 @pytest.mark.parametrize("psi", [0.0, 0.3, 1.0, 2.0, 3.2, 5.0, 9.0, 20.0, 60.0, 300.0, -4.0, 3000.0])
@@ -78,7 +97,7 @@ def test_pg1_distribution_vs_oracle(lib):
         out = _dbl(n)
         lib.h_pg_draws(psi, n, ctypes.c_uint64(99), out)
         x = np.frombuffer(out, dtype=np.float64)
-        y = np.array([orc.pg1_devroye(psi, rs) for _ in range(6000)])
+        y = np.array([orc.pg1_devroye(psi, rs) for _ in range(6000)])  # Devroye's original
         assert stats.ks_2samp(x, y).pvalue > 1e-3, psi
 
 

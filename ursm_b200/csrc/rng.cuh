@@ -8,6 +8,7 @@
 // as the counter, with cell/sample indices GLOBAL -- so a draw does not depend
 // on how cells are sharded over GPUs (check #4).
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -78,14 +79,49 @@ struct Philox {
     return r;
   }
 
-  // uniform on the open interval (0,1), 24-bit resolution, never 0 or 1
-  URSM_HD float uniform() { return ((next() >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+  // uniform on the open interval (0,1), 24-bit resolution, never 0 or 1 (k + 0.5 rounds
+  // to 2^24 for the largest k, hence the clamp)
+  URSM_HD float uniform() {
+    return fminf(((next() >> 8) + 0.5f) * 5.9604644775390625e-8f, 0.99999994f);
+  }
   // 53-bit-ish double uniform in (0,1) from two words
   URSM_HD double uniform_d() {
     uint32_t a = next(), b = next();
     return (((uint64_t)(a >> 5) << 26) + (b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
   }
 };
+
+// One Philox4x32-10 block as a pure function: counter (c0,c1,c2,c3) -> 4 words.
+// Bit-identical to the first refill of Philox(key, c0, c1, c2) when c3 == 0 and to
+// its (c3+1)-th refill in general.  The Gibbs kernel calls this once per sampling
+// ATTEMPT, with c3 = attempt index, so that every lane of a warp executes the
+// generator at full width (no data-dependent refill).
+URSM_HD void philox_block(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                          uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  uint32_t ka = (uint32_t)key, kb = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ ka;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ kb;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    ka += 0x9E3779B9u;
+    kb += 0xBB67AE85u;
+  }
+  r0 = c0;
+  r1 = c1;
+  r2 = c2;
+  r3 = c3;
+}
+
+// uniform on the open interval (0,1) from the top 24 bits of a word
+URSM_HD float u01(uint32_t w) {
+  return fminf(((w >> 8) + 0.5f) * 5.9604644775390625e-8f, 0.99999994f);
+}
 
 // Stream "purposes" folded into the third counter word (top 4 bits) so the
 // different consumers of one (cell, sweep) never share a counter.

@@ -19,6 +19,10 @@
 //    threads whose incoming sum moved by more than their margin re-scan (their
 //    uniforms are regenerated from the same Philox counter); repeat to the fixed
 //    point, which is the unique sequential solution.
+//  * draw_w (:318-323) is a rejection sampler; lanes of a warp run ATTEMPTS in lock
+//    step (one Philox block and a fixed amount of arithmetic each,
+//    samplers.cuh::pg_attempt) while every lane advances through its own genes, so
+//    divergence costs only the spread of the per-thread attempt totals.
 //  * draw_kappa_tau (:345-377): five block reductions in fp64, closed-form 2x2
 //    Cholesky draw by one thread, broadcast through shared memory.
 //  * update_suffStats (:245-270) needs w(t) together with the kappa/tau drawn
@@ -137,6 +141,8 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     const unsigned int gl = (unsigned int)(a.cell_offset + l);  // global cell id keys the RNG
     const float Rf = (float)a.R[l];
     const float* Acol = a.Aslot + (size_t)type * slots;
+    const int i0 = tid * g;                               // first gene of this thread's run
+    const int gcount = max(0, min(g, N - i0));
 
     // ---- init_gibbs (:212-225): S ~ Bern(1/2), S[Y>0] = 1, kappa/tau = prior means
     for (int i = tid; i < N; i += T) {
@@ -180,41 +186,69 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       double sw = 0, swa = 0, swaa = 0, as = 0, s_run = s_cur;
       int nS = 0;
       float margin = INFINITY;
-      // ---- draw_w (:318-323) + speculative draw_S (:326-342) + deferred fold
-      for (int j = 0; j < g; ++j) {
-        const int i = tid * g + j;
-        if (i >= N) break;
-        const int slot = j * T + tid;
-        const float av = Acol[slot];
-        const unsigned int f = fl_s[slot];
-        const unsigned int Sold = (f >> 1) & 1u, pos = f & 1u;
-        if (prev_ret) {  // update_suffStats (:245-270) of the previous sweep
-          const float wold = w_s[slot];
-          accA[slot] += ((float)Sold - 0.5f) * cA1 - wold * cA2;
-          accQ[slot] += cQ * wold;
-          cnt_s[slot] += (unsigned short)Sold;
+      // ---- draw_w (:318-323) + speculative draw_S (:326-342) + deferred fold.
+      // Attempt-synchronous: every trip of the while loop is ONE sampling attempt
+      // (one Philox block, fixed work) for the lane's current gene; a lane that
+      // accepts finishes the gene and moves to the next one of its run, so the
+      // rejection sampler never leaves lanes idle inside a gene.
+      const uint32_t ctr2 = kPurposeGene | (uint32_t)sweep;
+      int j = 0, attempt = 0, slot = tid;
+      bool have = gcount > 0;
+      float av = 0.f, psi = 0.f;
+      unsigned int f = 0u;
+      uint32_t rS = 0u;
+      PgTilt pg;
+#define URSM_LOAD_GENE()                                                       \
+  do {                                                                         \
+    av = Acol[slot];                                                           \
+    f = fl_s[slot];                                                            \
+    if (prev_ret) { /* update_suffStats (:245-270) of the previous sweep */    \
+      const float wold = w_s[slot];                                            \
+      const float Sf = (float)((f >> 1) & 1u);                                 \
+      accA[slot] += (Sf - 0.5f) * cA1 - wold * cA2;                            \
+      accQ[slot] += cQ * wold;                                                 \
+      cnt_s[slot] += (unsigned short)((f >> 1) & 1u);                          \
+    }                                                                          \
+    psi = fmaf(ft, av, fk);                                                    \
+    pg = pg_tilt(psi);                                                         \
+  } while (0)
+      if (have) URSM_LOAD_GENE();
+      while (__any_sync(0xffffffffu, have)) {
+        if (have) {
+          uint32_t r0, r1, r2, r3;
+          philox_block(a.key, (uint32_t)(i0 + j), gl, ctr2, (uint32_t)attempt, r0, r1, r2, r3);
+          if (attempt == 0) rS = r3;  // word 3 of the first attempt: the S uniform
+          float x;
+          if (pg_attempt(pg, u01(r0), u01(r1), u01(r2), x)) {
+            const float wn = 0.25f * x;
+            w_s[slot] = wn;
+            const double wd = wn, ad = av;
+            sw += wd;
+            swa += wd * ad;
+            swaa += wd * ad * ad;
+            const unsigned int Sold = (f >> 1) & 1u, pos = f & 1u;
+            const float Tth = s_threshold(psi, u01(rS), av, Rf);
+            unsigned int Snew = 1u;
+            if (!pos) {
+              const double so = s_run - (Sold ? ad : 0.0);
+              Snew = (so > (double)Tth) ? 1u : 0u;
+              margin = fminf(margin, fabsf((float)(so - (double)Tth)));
+              s_run = so + (Snew ? ad : 0.0);
+            }
+            fl_s[slot] = (unsigned char)(pos | (Snew << 1) | (Sold << 2));
+            nS += (int)Snew;
+            if (Snew) as += ad;
+            ++j;
+            slot += T;
+            attempt = 0;
+            have = j < gcount;
+            if (have) URSM_LOAD_GENE();
+          } else {
+            ++attempt;
+          }
         }
-        const float psi = fmaf(ft, av, fk);
-        Philox rng(a.key, (uint32_t)i, gl, kPurposeGene | (uint32_t)sweep);
-        const float u = rng.uniform();  // first word of the stream: the S uniform
-        const float wn = pg1_devroye(psi, rng);
-        w_s[slot] = wn;
-        const double wd = wn, ad = av;
-        sw += wd;
-        swa += wd * ad;
-        swaa += wd * ad * ad;
-        unsigned int Snew = 1u;
-        if (!pos) {
-          const float Tth = s_threshold(psi, u, av, Rf);
-          const double so = s_run - (Sold ? ad : 0.0);
-          Snew = (so > (double)Tth) ? 1u : 0u;
-          margin = fminf(margin, fabsf((float)(so - (double)Tth)));
-          s_run = so + (Snew ? ad : 0.0);
-        }
-        fl_s[slot] = (unsigned char)(pos | (Snew << 1) | (Sold << 2));
-        nS += (int)Snew;
-        if (Snew) as += ad;
       }
+#undef URSM_LOAD_GENE
       // ---- exact sequential semantics: fixed point over the incoming prefix sums
       double delta = s_run - s_cur, used_in = s_cur;
       int rounds = 0;
@@ -240,8 +274,9 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
             const unsigned int Sold = (f >> 2) & 1u, pos = f & 1u;
             unsigned int Snew = 1u;
             if (!pos) {
-              Philox rng(a.key, (uint32_t)i, gl, kPurposeGene | (uint32_t)sweep);
-              const float u = rng.uniform();
+              uint32_t r0, r1, r2, r3;
+              philox_block(a.key, (uint32_t)i, gl, ctr2, 0u, r0, r1, r2, r3);
+              const float u = u01(r3);
               const float psi = fmaf(ft, av, fk);
               const float Tth = s_threshold(psi, u, av, Rf);
               const double so = s_run - (Sold ? ad : 0.0);
