@@ -61,6 +61,7 @@ def hostlib():
     L.h_s_threshold.argtypes = [dbl] * 4
     L.h_pg_draws.argtypes = [dbl, i32, u64, vp]
     L.h_binomial.argtypes = [i32, dbl, i32, u64, vp]
+    L.h_binomial_f32.argtypes = [i32, dbl, i32, u64, vp]
     L.h_gamma.argtypes = [dbl, i32, u64, vp]
     L.h_gene_uniforms.argtypes = [u64, u32, u32, i32, vp]
     L.h_cell_normals.argtypes = [u64, u32, u32, vp]

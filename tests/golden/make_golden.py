@@ -221,8 +221,82 @@ def kat_sconly(ref, demo):
     return out
 
 
+def _use_c_pg(ref):
+    """Statistical fixtures need long chains: swap the shim's sampler for the compiled
+    restatement (oracle/pg_devroye.c) -- same distribution, ~100x faster."""
+    ref["e_step_gibbs"].ppg.PyPolyaGamma = orc.CPGSampler
+    ref["e_step_gibbs"].ppg.pgdrawvpar = orc.pgdrawv_c
+
+
+def stat_chains(ref):
+    """Long Gibbs chains of the REFERENCE classes on a small problem, several independent
+    repeats: posterior-mean statistics with their between-chain spread.  The CUDA chains
+    must agree within Monte-Carlo error (north-star check #2/#3)."""
+    _use_c_pg(ref)
+    sim = orc.simulate(N=60, K=3, L=12, M=6, seed=11, anchor=1, anti=1)
+    Y, X, G = sim["Y"], sim["X"], sim["G"]
+    itype = [np.where(G == k)[0] for k in range(3)]
+    A = orc.init_A(Y, X, 3, itype, 1e-6)
+    pk, pt, alpha = np.array([-1.0, 0.25]), np.array([60.0, 36.0]), np.array([1.5, 1.0, 2.0])
+    burnin, sample, reps = 200, 3000, 12
+    keys_sc = ("exp_S", "exp_kappa", "exp_tau", "exp_kappasq", "exp_tausq", "coeffA", "coeffAsq",
+               "exp_elbo_const")
+    keys_bk = ("exp_Zik", "exp_Zjk", "exp_logW", "exp_W")
+    acc = {k: [] for k in keys_sc + keys_bk}
+    for rep in range(reps):
+        np.random.seed(1000 + rep)
+        sc = ref["e_step_gibbs"].LogitNormalGibbs_SC(A, pk, pt, Y, G, itype)
+        sc.init_gibbs()
+        sc.gibbs(burnin=burnin, sample=sample, thin=1)
+        for k in keys_sc:
+            acc[k].append(np.array(sc.suff_stats[k], dtype=float))
+        bk = ref["e_step_gibbs"].LogitNormalGibbs_BK(A, alpha, X, None)
+        bk.init_gibbs()
+        bk.gibbs(burnin=burnin, sample=sample, thin=1, mean_approx=False)
+        for k in keys_bk:
+            acc[k].append(np.array(bk.suff_stats[k], dtype=float))
+    out = dict(Y=Y, X=X, G=G, A=A, pkappa=pk, ptau=pt, alpha=alpha, burnin=burnin, sample=sample,
+               reps=reps)
+    for k, v in acc.items():
+        v = np.array(v)
+        out["mean_" + k] = v.mean(axis=0)
+        out["sd_" + k] = v.std(axis=0, ddof=1)
+    return out
+
+
+def demo_fits(ref, demo):
+    """Reruns of the reference's `make run` configuration (burnin 10 / sample 20 / EM 10,
+    joint demo data, default mean-approx bulk): estimates with their run-to-run spread."""
+    _use_c_pg(ref)
+    keep = dict(A=[], alpha=[], pkappa=[], ptau=[], path=[], exp_W=[], exp_S=[], exp_kappa=[],
+                exp_tau=[])
+    for rep in range(6):
+        np.random.seed(500 + rep)
+        gem = ref["gem"].LogitNormalGEM(BKexpr=demo["X"], SCexpr=demo["Y"], K=3, G=demo["G"],
+                                        burnin=10, sample=20, thin=1, bk_mean_approx=True,
+                                        MLE_CONV=1e-6, MLE_maxiter=500, EM_CONV=1e-6, EM_maxiter=10)
+        path = gem.gem()[3]
+        keep["A"].append(gem.A)
+        keep["alpha"].append(gem.alpha)
+        keep["pkappa"].append(gem.pkappa)
+        keep["ptau"].append(gem.ptau)
+        keep["path"].append(path)
+        keep["exp_W"].append(gem.suff_stats["exp_W"])
+        keep["exp_S"].append(gem.suff_stats["exp_S"])
+        keep["exp_kappa"].append(gem.suff_stats["exp_kappa"])
+        keep["exp_tau"].append(gem.suff_stats["exp_tau"])
+    out = {}
+    for k, v in keep.items():
+        v = np.array(v)
+        out["mean_" + k] = v.mean(axis=0)
+        out["sd_" + k] = v.std(axis=0, ddof=1)
+    out["reps"] = 6
+    return out
+
+
 def main():
-    ref_dir = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    args = [x for x in sys.argv[1:] if not x.startswith("--")]
+    ref_dir = args[0] if args else "/root/reference"
     ref = load_reference(ref_dir)
     demo = demo_data(ref_dir)
     np.savez_compressed(os.path.join(HERE, "demo_data.npz"), **demo)
@@ -231,6 +305,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "kat_sc.npz"), **kat_sc(ref, demo))
     np.savez_compressed(os.path.join(HERE, "kat_sconly.npz"), **kat_sconly(ref, demo))
     np.savez_compressed(os.path.join(HERE, "kat_gibbs_seeded.npz"), **kat_gibbs_seeded(ref))
+    if "--no-stat" not in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "stat_chains.npz"), **stat_chains(ref))
+        np.savez_compressed(os.path.join(HERE, "stat_demo_fits.npz"), **demo_fits(ref, demo))
     k = np.load(os.path.join(HERE, "kat_sc.npz"))
     b = np.load(os.path.join(HERE, "kat_bulk.npz"))
     print("KAT-B  path_elbo", b["path_elbo"])

@@ -28,6 +28,12 @@ void h_binomial(int n, double p, int count, uint64_t seed, int* out) {
     out[i] = binomial(n, p, g);
   }
 }
+void h_binomial_f32(int n, double p, int count, uint64_t seed, int* out) {
+  for (int i = 0; i < count; ++i) {
+    Philox g(seed, (uint32_t)i, 5u, 0u);
+    out[i] = binomial_f32(n, (float)p, (float)(1.0 - p), g);
+  }
+}
 void h_gamma(double shape, int count, uint64_t seed, double* out) {
   for (int i = 0; i < count; ++i) {
     Philox g(seed, (uint32_t)i, 2u, 0u);

@@ -121,11 +121,14 @@ def test_s_threshold_is_the_bernoulli(lib):
 
 
 @pytest.mark.parametrize("n,p", [(1, 0.3), (7, 0.5), (40, 0.02), (50, 0.9), (300, 0.2),
-                                 (5000, 0.013), (100000, 0.4), (2000000, 0.001), (3000, 0.97)])
-def test_binomial_pmf(lib, n, p):
+                                 (5000, 0.013), (100000, 0.4), (2000000, 0.001), (3000, 0.97),
+                                 (155, 0.2), (64, 0.5), (1000, 0.031), (20000, 0.5)])
+@pytest.mark.parametrize("which", ["f64", "f32_state_machine"])
+def test_binomial_pmf(lib, n, p, which):
     cnt = 200000
     out = (ctypes.c_int * cnt)()
-    lib.h_binomial(n, p, cnt, ctypes.c_uint64(n * 7 + 1), out)
+    fn = lib.h_binomial if which == "f64" else lib.h_binomial_f32
+    fn(n, p, cnt, ctypes.c_uint64(n * 7 + 1), out)
     x = np.frombuffer(out, dtype=np.int32)
     assert x.min() >= 0 and x.max() <= n
     assert abs(x.mean() - n * p) < 4.5 * np.sqrt(n * p * (1 - p) / cnt)

@@ -26,6 +26,7 @@ struct BkTileArgs {
   const float* X;      // [M][N]
   const double* A;     // [K][N]
   const double* W;     // [M][K]
+  const int* perm;     // [N] split kernel: sorted position -> gene (X is column-sorted)
   long long M;
   int N, K;
   long long sample_offset;
@@ -119,6 +120,176 @@ __global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
       if (accI[k] != 0.0) atomicAdd(&a.sumI[(size_t)k * N + gi], accI[k] * a.scaleI);
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// draw_Z (:132-138) for one Gibbs sweep: Z_ji. ~ Mult(X_ji, W_.j A_i. / AW_ij) as a
+// chain of K-1 conditional binomials.  A thread owns one gene and walks the CTA's
+// chunk of bulk samples; the binomials are data-dependent loops (inversion takes
+// ~n p steps, BTRS is a rejection sampler), so lanes are DESYNCHRONISED: every trip of
+// the warp loop gives each lane a bounded slice of work on its own current
+// (sample, type) item -- 8 inversion steps or one BTRS attempt -- and a lane that
+// finishes an item moves on by itself (samplers.cuh::BinomState).  Z is consumed on
+// the spot: sum_i Z_jik -> shared-memory integer atomics (-> one global atomic per
+// CTA, sample, type), sum_j Z_jik -> per-thread shared-memory counters, flushed once.
+// Arithmetic is fp32 on ratios of positive suffix sums (no cancellation); counts are
+// exact integers.
+// ---------------------------------------------------------------------------
+constexpr int kSplitThreads = 256;
+
+__global__ void __launch_bounds__(kSplitThreads) bk_split_kernel(BkTileArgs a) {
+  extern __shared__ __align__(16) unsigned char split_smem[];
+  const int tid = threadIdx.x;
+  const int K = a.K, N = a.N;
+  const long long j0 = (long long)blockIdx.y * a.chunk;
+  const long long j1 = min(a.M, j0 + a.chunk);
+  const int nloc = (int)(j1 - j0);
+  float* Wsm = reinterpret_cast<float*>(split_smem);                      // [chunk][K]
+  unsigned int* Jsm = reinterpret_cast<unsigned int*>(Wsm + a.chunk * K);  // [chunk][K]
+  float* As = reinterpret_cast<float*>(Jsm + a.chunk * K);                 // [K][T]
+  float* suf = As + K * kSplitThreads;                                     // [K+1][T]
+  unsigned int* accI = reinterpret_cast<unsigned int*>(suf + (K + 1) * kSplitThreads);  // [K][T]
+  for (int t = tid; t < nloc * K; t += kSplitThreads) {
+    Wsm[t] = (float)a.W[j0 * K + t];
+    Jsm[t] = 0u;
+  }
+  // X is stored with its columns sorted by total count, so the lanes of a warp hold
+  // genes of similar depth and their data-dependent binomial loops take similar time;
+  // `gene` is the original index (it keys the RNG: results do not depend on the sort)
+  const int gi = blockIdx.x * kSplitThreads + tid;
+  const bool in = gi < N;
+  const int gene = in ? a.perm[gi] : 0;
+  for (int k = 0; k < K; ++k) {
+    As[k * kSplitThreads + tid] = in ? (float)a.A[(size_t)k * N + gene] : 0.f;
+    accI[k * kSplitThreads + tid] = 0u;
+  }
+  suf[K * kSplitThreads + tid] = 0.f;
+  __syncthreads();
+
+  // per-lane state
+  int jl = in ? 0 : nloc;  // current sample (local)
+  int k = 0, rem = 0, nw = 0;
+  bool fresh = true;       // need to open the entry (jl, gi)
+  bool item = false;       // a binomial is in flight
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  BinomState b;
+  b.mode = kBinDone;
+  const uint32_t ctr2 = kPurposeBulkZ | a.sweep;
+
+  auto next_uniform = [&]() -> float {
+    if ((nw & 3) == 0)
+      philox_block(a.key, (uint32_t)gene, (uint32_t)(a.sample_offset + j0 + jl), ctr2,
+                   (uint32_t)(nw >> 2), w0, w1, w2, w3);
+    const int sel = nw & 3;
+    ++nw;
+    const uint32_t w = sel == 0 ? w0 : (sel == 1 ? w1 : (sel == 2 ? w2 : w3));
+    return u01(w);
+  };
+
+  while (__any_sync(0xffffffffu, jl < nloc)) {
+    if (jl < nloc) {
+      if (fresh) {
+        const float xf = a.X[(size_t)(j0 + jl) * N + gi];
+        if (xf == 0.f) {  // nothing to split
+          ++jl;
+        } else {
+          rem = (int)xf;
+          const float* Wj = Wsm + jl * K;
+          float acc = 0.f;
+          for (int kk = K - 1; kk >= 0; --kk) {  // suffix sums of W_kj A_ik (all positive)
+            acc += Wj[kk] * As[kk * kSplitThreads + tid];
+            suf[kk * kSplitThreads + tid] = acc;
+          }
+          k = 0;
+          nw = 0;
+          fresh = false;
+          item = false;
+        }
+      }
+      if (!fresh) {
+        if (!item) {
+          if (k == K - 1 || rem == 0) {
+            // the last type takes what is left (also closes an exhausted entry)
+            if (rem > 0) {
+              atomicAdd(&Jsm[jl * K + k], (unsigned int)rem);
+              accI[k * kSplitThreads + tid] += (unsigned int)rem;
+            }
+            ++jl;
+            fresh = true;
+          } else {
+            const float sk = suf[k * kSplitThreads + tid];
+            const float sn = suf[(k + 1) * kSplitThreads + tid];
+            const float pc = sn / sk;                       // P(not type k | not yet assigned)
+            const float pk = (sk - sn) / sk;
+            // W_kj A_ik / suffix, formed from the product itself when it is the small side
+            const float qk = Wsm[jl * K + k] * As[k * kSplitThreads + tid];
+            binom_begin(b, rem, (pk < 0.5f) ? qk / sk : pk, pc, next_uniform());
+            item = true;
+          }
+        }
+        if (item) {
+          if (b.mode == kBinInv) {
+            binom_inv_steps(b, 8);
+          } else if (b.mode == kBinBtrs) {
+            const float U = next_uniform(), V = next_uniform();
+            binom_btrs_attempt(b, U, V);
+          } else if (b.mode == kBinRetry) {
+            binom_inv_start(b, next_uniform());
+          }
+          if (b.mode == kBinDone) {
+            const int z = b.result;
+            if (z > 0) {
+              atomicAdd(&Jsm[jl * K + k], (unsigned int)z);
+              accI[k * kSplitThreads + tid] += (unsigned int)z;
+              rem -= z;
+            }
+            ++k;
+            item = false;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < nloc * K; t += kSplitThreads)
+    if (Jsm[t] != 0u) atomicAdd(&a.sumJ[j0 * K + t], (double)Jsm[t]);
+  if (in && a.accumulate_I) {
+    for (int kk = 0; kk < K; ++kk) {
+      const unsigned int v = accI[kk * kSplitThreads + tid];
+      if (v != 0u) atomicAdd(&a.sumI[(size_t)kk * N + gene], (double)v * a.scaleI);
+    }
+  }
+}
+
+static void bk_launch_split(BkShard* b, BkTileArgs& a, cudaStream_t st) {
+  a.X = b->Xs.p;
+  a.perm = b->perm.p;
+  a.A = b->A.p;
+  a.W = b->W.p;
+  a.M = b->M;
+  a.N = b->N;
+  a.K = b->K;
+  a.sample_offset = b->sample_offset;
+  const int K = b->K;
+  const int gx = (b->N + kSplitThreads - 1) / kSplitThreads;
+  const size_t per_thread = (size_t)(3 * K + 1) * kSplitThreads * 4;
+  // a chunk's W rows and per-sample sums (8 B per sample and type) share the CTA's smem
+  const long long max_chunk = std::max<long long>(1, (long long)(24 * 1024) / (8 * (long long)K));
+  long long want_y = std::max<long long>(1, (long long)(4 * b->num_sms + gx - 1) / gx);
+  want_y = std::max<long long>(want_y, (b->M + max_chunk - 1) / max_chunk);
+  long long ny = std::min<long long>(b->M, want_y);
+  a.chunk = (int)((b->M + ny - 1) / ny);
+  ny = (b->M + a.chunk - 1) / a.chunk;
+  URSM_REQUIRE(ny <= 65535, "bulk split kernel: too many sample chunks");
+  const size_t smem = per_thread + (size_t)a.chunk * K * 8;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    URSM_CUDA(cudaFuncSetAttribute(bk_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    configured = smem;
+  }
+  bk_split_kernel<<<dim3(gx, (unsigned)ny), kSplitThreads, smem, st>>>(a);
+  URSM_LAUNCH_CHECK();
 }
 
 // W_kj <- W_kj * numer_jk + alpha_k - 1, renormalised over k (:159-164)
@@ -235,6 +406,45 @@ static void bk_time_begin(BkShard* b, cudaStream_t st) {
 static void bk_time_end(BkShard* b, cudaStream_t st) {
   URSM_CUDA(cudaEventRecord(b->ev1, st));
   b->timed = true;
+}
+
+__global__ void bk_colsum_kernel(const float* X, long long M, int N, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double s = 0.0;
+  for (long long j = 0; j < M; ++j) s += (double)X[(size_t)j * N + i];
+  out[i] = s;
+}
+
+__global__ void bk_gather_cols_kernel(const float* X, const int* perm, long long M, int N,
+                                      float* Xs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long j = blockIdx.y;
+  if (i < N) Xs[(size_t)j * N + i] = X[(size_t)j * N + perm[i]];
+}
+
+// column-sorted copy of X for the Gibbs split kernel (X never changes during a fit)
+static void bk_build_sorted(BkShard* b) {
+  const int N = b->N;
+  DevBuf<double> cs;
+  cs.alloc(N);
+  bk_colsum_kernel<<<(N + 255) / 256, 256>>>(b->X, b->M, N, cs.p);
+  URSM_LAUNCH_CHECK();
+  std::vector<double> h(N);
+  URSM_CUDA(cudaMemcpy(h.data(), cs.p, N * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<int> perm(N);
+  for (int i = 0; i < N; ++i) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return h[x] > h[y]; });
+  b->perm.alloc(N);
+  URSM_CUDA(cudaMemcpy(b->perm.p, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+  b->Xs.alloc((size_t)b->M * N);
+  for (long long j0 = 0; j0 < b->M; j0 += 65535) {
+    const unsigned rows = (unsigned)std::min<long long>(65535, b->M - j0);
+    bk_gather_cols_kernel<<<dim3((N + 255) / 256, rows), 256>>>(b->X + (size_t)j0 * N, b->perm.p,
+                                                               rows, N, b->Xs.p + (size_t)j0 * N);
+    URSM_LAUNCH_CHECK();
+  }
+  URSM_CUDA(cudaDeviceSynchronize());
 }
 
 static void bk_finish_create(BkShard* b) {
@@ -399,6 +609,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   URSM_REQUIRE(b && d_stats, "ursm_bk_gibbs: bad argument");
   URSM_REQUIRE(b->has_params && b->has_state, "ursm_bk_gibbs: params/state not set");
   URSM_REQUIRE(burnin >= 0 && sample >= 1 && thin >= 1, "ursm_bk_gibbs: bad sweep counts");
+  if (!b->Xs.p) bk_build_sorted(b);  // once per fit, first Gibbs E-step only
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned mb = (unsigned)((b->M + 127) / 128);
   const unsigned long long key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1) + 0x5bd1e995ull;
@@ -427,7 +638,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
     a.accumulate_I = retained ? 1 : 0;
     a.key = key;
     a.sweep = (unsigned)sweep;
-    bk_launch_tile<2>(b, a, st);
+    bk_launch_split(b, a, st);
     if (!freezeZ) std::swap(b->nA.p, b->nB.p);
     if (freezeZ && retained) {
       // frozen-Z moment test: E[Z_jk] accumulates the fixed sums

@@ -19,6 +19,17 @@
 
 namespace ursm {
 
+// uniform on (0,1) from the top 23 bits of a word (see Philox::uniform)
+URSM_HD float u01(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(0x3f800000u | (w >> 9)) - 0.99999994f;
+#else
+  union { uint32_t i; float f; } c;
+  c.i = 0x3f800000u | (w >> 9);
+  return c.f - 0.99999994f;
+#endif
+}
+
 struct Philox {
   uint32_t c0, c1, c2, c3;  // counter; c3 is the running block index
   uint32_t k0, k1;          // key
@@ -79,11 +90,9 @@ struct Philox {
     return r;
   }
 
-  // uniform on the open interval (0,1), 24-bit resolution, never 0 or 1 (k + 0.5 rounds
-  // to 2^24 for the largest k, hence the clamp)
-  URSM_HD float uniform() {
-    return fminf(((next() >> 8) + 0.5f) * 5.9604644775390625e-8f, 0.99999994f);
-  }
+  // uniform on the open interval (0,1): 23 random mantissa bits + 2^-24, i.e. the
+  // centres k 2^-23 + 2^-24 of 2^23 equal cells -- never 0 or 1, no int->float convert
+  URSM_HD float uniform() { return u01(next()); }
   // 53-bit-ish double uniform in (0,1) from two words
   URSM_HD double uniform_d() {
     uint32_t a = next(), b = next();
@@ -116,11 +125,6 @@ URSM_HD void philox_block(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, u
   r1 = c1;
   r2 = c2;
   r3 = c3;
-}
-
-// uniform on the open interval (0,1) from the top 24 bits of a word
-URSM_HD float u01(uint32_t w) {
-  return fminf(((w >> 8) + 0.5f) * 5.9604644775390625e-8f, 0.99999994f);
 }
 
 // Stream "purposes" folded into the third counter word (top 4 bits) so the

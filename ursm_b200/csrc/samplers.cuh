@@ -13,12 +13,17 @@
 
 namespace ursm {
 
+// fast single-precision intrinsics on the device (2-ulp class), libm on the host
 #if defined(__CUDA_ARCH__)
 #define URSM_EXPF(x) __expf(x)
 #define URSM_LOGF(x) __logf(x)
+#define URSM_DIV(a, b) __fdividef((a), (b))
+#define URSM_RSQRT(x) rsqrtf(x)
 #else
 #define URSM_EXPF(x) expf(x)
 #define URSM_LOGF(x) logf(x)
+#define URSM_DIV(a, b) ((a) / (b))
+#define URSM_RSQRT(x) (1.0f / sqrtf(x))
 #endif
 
 // ---------------------------------------------------------------------------
@@ -57,43 +62,45 @@ namespace ursm {
 #define URSM_PG_C0 0.10564977366685535f  // Phi(-1/sqrt t)
 
 struct PgTilt {
-  float z, fz, hz2, mass_right, mu;
+  float hz2, inv_fz, mass_right, inv_left, mu;
   bool ig;  // left piece by inverse Gaussian (z >= 1/t) or by truncated Levy
 };
 
 URSM_HD PgTilt pg_tilt(float psi) {
   PgTilt g;
   const float t = URSM_PG_T;
-  g.z = 0.5f * fabsf(psi);
-  g.hz2 = 0.5f * g.z * g.z;
-  g.fz = 1.2337005501361697f + g.hz2;
-  g.ig = g.z >= URSM_PG_INV_T;
+  const float z = 0.5f * fabsf(psi);
+  g.hz2 = 0.5f * z * z;
+  const float fz = 1.2337005501361697f + g.hz2;
+  g.inv_fz = URSM_DIV(1.0f, fz);
+  g.ig = z >= URSM_PG_INV_T;
   // q/p with the cosh(z) factors cancelled; the exponent is >= 0.008 for every z
-  const float ex = g.ig ? (t * g.fz - g.z) : (t * g.fz);
+  const float ex = g.ig ? (t * fz - z) : (t * fz);
   const float c = g.ig ? 1.2732395447351628f /* 4/pi */ : 0.26903493f /* 2 q0/pi */;
-  const float qdivp = c * g.fz * URSM_EXPF(ex);  // +inf for large z -> mass 0
-  g.mass_right = 1.0f / (1.0f + qdivp);
-  g.mu = 1.0f / fmaxf(g.z, 1e-20f);
+  const float qdivp = c * fz * URSM_EXPF(ex);  // +inf for large z -> mass 0
+  g.mass_right = URSM_DIV(1.0f, 1.0f + qdivp);
+  g.inv_left = URSM_DIV(1.0f, 1.0f - g.mass_right);
+  g.mu = URSM_DIV(1.0f, fmaxf(z, 1e-20f));
   return g;
 }
 
-// Z^2 for Z = Phi^{-1}(v), v in (0,1): Giles' single-precision erfinv (2012),
-// both branches evaluated (the tail branch is needed for 1.6% of the truncated
-// draws, which would otherwise diverge in 40% of the warps)
-URSM_HD float ndtri_sq(float v) {
-  const float x = 2.0f * v - 1.0f;
-  float w = -URSM_LOGF(4.0f * v * (1.0f - v));
-  float wc = w - 2.5f;
-  float p = 2.81022636e-08f;
-  p = fmaf(p, wc, 3.43273939e-07f);
-  p = fmaf(p, wc, -3.5233877e-06f);
-  p = fmaf(p, wc, -4.39150654e-06f);
-  p = fmaf(p, wc, 0.00021858087f);
-  p = fmaf(p, wc, -0.00125372503f);
-  p = fmaf(p, wc, -0.00417768164f);
-  p = fmaf(p, wc, 0.246640727f);
-  p = fmaf(p, wc, 1.50140941f);
-  float wt = sqrtf(fmaxf(w, 5.0f)) - 3.0f;
+// erfinv(x)/x as a function of w = -log(1 - x^2): Giles' single-precision
+// approximation (2012); the tail branch (w >= 5, |x| > 0.9966) is a real branch, taken
+// by about 1% of the lanes
+URSM_HD float erfinv_over_x(float w) {
+  if (w < 5.0f) {
+    const float wc = w - 2.5f;
+    float p = 2.81022636e-08f;
+    p = fmaf(p, wc, 3.43273939e-07f);
+    p = fmaf(p, wc, -3.5233877e-06f);
+    p = fmaf(p, wc, -4.39150654e-06f);
+    p = fmaf(p, wc, 0.00021858087f);
+    p = fmaf(p, wc, -0.00125372503f);
+    p = fmaf(p, wc, -0.00417768164f);
+    p = fmaf(p, wc, 0.246640727f);
+    return fmaf(p, wc, 1.50140941f);
+  }
+  const float wt = w * URSM_RSQRT(w) - 3.0f;
   float r = -0.000200214257f;
   r = fmaf(r, wt, 0.000100950558f);
   r = fmaf(r, wt, 0.00134934322f);
@@ -102,8 +109,12 @@ URSM_HD float ndtri_sq(float v) {
   r = fmaf(r, wt, -0.0076224613f);
   r = fmaf(r, wt, 0.00943887047f);
   r = fmaf(r, wt, 1.00167406f);
-  r = fmaf(r, wt, 2.83297682f);
-  const float e = ((w < 5.0f) ? p : r) * x;  // erfinv(2v - 1)
+  return fmaf(r, wt, 2.83297682f);
+}
+
+// Z^2 for Z = Phi^{-1}(v), v in (0,1)
+URSM_HD float ndtri_sq(float v) {
+  const float e = erfinv_over_x(-URSM_LOGF(4.0f * v * (1.0f - v))) * (2.0f * v - 1.0f);
   return 2.0f * e * e;
 }
 
@@ -111,20 +122,30 @@ URSM_HD float ndtri_sq(float v) {
 URSM_HD bool pg_attempt(const PgTilt& g, float u0, float u1, float u2, float& x) {
   const float t = URSM_PG_T;
   const bool right = u0 < g.mass_right;
+  // one logarithm serves both pieces: Exp(1) = -log u1 on the right, the erfinv
+  // argument -log(1 - (2v-1)^2) on the left
+  const float v = g.ig ? u1 : u1 * URSM_PG_C0;
+  const float lg = -URSM_LOGF(right ? u1 : 4.0f * v * (1.0f - v));
   // piece R
-  const float xr = t - URSM_LOGF(u1) / g.fz;
-  // piece L
-  const float zn2 = ndtri_sq(g.ig ? u1 : u1 * URSM_PG_C0);
+  const float xr = fmaf(lg, g.inv_fz, t);
+  // piece L: zn2 = Z^2, Z = Phi^{-1}(v)
+  const float e = erfinv_over_x(lg) * (2.0f * v - 1.0f);
+  const float zn2 = 2.0f * e * e;
+  //   inverse Gaussian(mu, 1) by Michael-Schucany-Haas (smaller root written
+  //   without cancellation); the root choice reuses u0 | left
   const float my = g.mu * zn2;
-  float xi = g.mu / (1.0f + 0.5f * my + 0.5f * sqrtf(4.0f * my + my * my));
-  const float up = (u0 - g.mass_right) / (1.0f - g.mass_right);  // uniform given "left"
-  if (up * (g.mu + xi) > g.mu) xi = g.mu * g.mu / xi;
-  const float xl = g.ig ? xi : 1.0f / zn2;
+  const float disc = fmaf(my, my, 4.0f * my);
+  float xi = URSM_DIV(g.mu, 1.0f + 0.5f * my + 0.5f * disc * URSM_RSQRT(fmaxf(disc, 1e-30f)));
+  const float up = (u0 - g.mass_right) * g.inv_left;  // uniform given "left"
+  if (up * (g.mu + xi) > g.mu) xi = URSM_DIV(g.mu * g.mu, xi);
+  //   truncated Levy: x = 1/Z^2
+  const float inv_xl = g.ig ? URSM_DIV(1.0f, xi) : zn2;
+  const float xl = g.ig ? xi : URSM_DIV(1.0f, zn2);
   x = right ? xr : xl;
-  const float q = URSM_EXPF(right ? -9.869604401089358f * x : -4.0f / x);
+  const float q = URSM_EXPF(right ? -9.869604401089358f * xr : -4.0f * inv_xl);
   const float q3 = q * q * q;
   const float series = 1.0f - 3.0f * q + 5.0f * q3 - 7.0f * q3 * q3;
-  const float tilt = right ? 1.0f : (g.ig ? ((xl <= t) ? 1.0f : 0.0f) : URSM_EXPF(-g.hz2 * xl));
+  const float tilt = (right || g.ig) ? ((right || xl <= t) ? 1.0f : 0.0f) : URSM_EXPF(-g.hz2 * xl);
   return u2 <= tilt * series;
 }
 
@@ -147,13 +168,23 @@ URSM_HD float pg1_draw(float psi, RNG& rng) {
 // R == 0 (cell without reads; the reference's `sum_other == 0` branch,
 // e_step_gibbs.py:334-335) decides on logit(u) < psi alone: T = -inf / +inf.
 // ---------------------------------------------------------------------------
-URSM_HD float s_threshold(float psi, float u, float a, float R) {
-  float lg = URSM_LOGF(u / (1.0f - u));  // logit(u); 1-u is exact to 2^-25 for 24-bit u
-  float D = psi - lg;
+// expm1(x) for x > 0: Taylor to x^6 below 1/4 (relative error < 5e-8), exp - 1 above
+URSM_HD float expm1_pos(float x) {
+  const float p = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.0f / 720, 1.0f / 120), 1.0f / 24),
+                                          1.0f / 6), 0.5f), 1.0f);
+  return (x < 0.25f) ? p : URSM_EXPF(x) - 1.0f;
+}
+
+// `invR` = 1/R for R > 0, anything for R <= 0
+URSM_HD float s_threshold(float psi, float u, float a, float R, float invR) {
+  const float lg = URSM_LOGF(URSM_DIV(u, 1.0f - u));  // logit(u); 1-u is exact for 23-bit u
+  const float D = psi - lg;
   if (R <= 0.0f) return (D > 0.0f) ? -INFINITY : INFINITY;
   if (D <= 0.0f) return INFINITY;
-  float e = expm1f(D / R);
-  return a / e;  // e == +inf -> 0: always on
+  return URSM_DIV(a, expm1_pos(D * invR));  // expm1 == +inf -> 0: always on
+}
+URSM_HD float s_threshold(float psi, float u, float a, float R) {
+  return s_threshold(psi, u, a, R, R > 0.0f ? 1.0f / R : 0.0f);
 }
 
 // ---------------------------------------------------------------------------
@@ -300,6 +331,147 @@ URSM_HD int binomial(int n, double p, RNG& rng) {
   double r = flip ? 1.0 - p : p;
   int x = (n * r <= 30.0) ? binomial_inversion(n, r, rng) : binomial_btpe(n, r, rng);
   return flip ? n - x : x;
+}
+
+// ---------------------------------------------------------------------------
+// Binomial(n, p) as a resumable state machine in fp32 for the bulk split kernel
+// (csrc/bk_gibbs.cu::bk_split_kernel): lanes of a warp interleave "a few inversion
+// steps" / "one BTRS attempt" instead of each running its own data-dependent loop.
+//   n r <= 14  sequential inversion from 0 (as binomial_inversion above), fp32;
+//   n r  > 14  BTRS, Hormann's transformed rejection with squeeze (1993): the
+//              86% quick-accept path in fp32, the exact log-ratio test in fp64.
+// `p` and its complement are passed separately (both are ratios of positive sums in
+// the caller), so 1 - p is never formed by subtraction.
+// ---------------------------------------------------------------------------
+enum : int { kBinDone = 0, kBinInv = 1, kBinBtrs = 2, kBinRetry = 3 };
+
+struct BinomState {
+  int n, x, mode, result, bound;
+  float r, rc, px, u, s, c;  // s = r/(1-r), c = (n+1) s
+  bool flip;
+};
+
+// n r above which BTRS replaces inversion (BTRS needs n r >= 10)
+#define URSM_BINOM_INV_MAX 14.0f
+
+URSM_HD void binom_inv_start(BinomState& b, float u) {
+  // pmf(0) = (1-r)^n; n r <= 14 keeps it above 1e-7
+  b.px = URSM_EXPF((float)b.n * log1pf(-b.r));
+  b.x = 0;
+  b.u = u;
+  b.mode = kBinInv;
+}
+
+URSM_HD void binom_begin(BinomState& b, int n, float p, float pc, float u) {
+  b.n = n;
+  b.flip = p > 0.5f;
+  b.r = b.flip ? pc : p;
+  b.rc = b.flip ? p : pc;
+  b.result = 0;
+  if (n <= 0 || !(b.r > 0.0f)) {  // degenerate: everything to one side
+    b.result = b.flip ? n : 0;
+    b.mode = kBinDone;
+    return;
+  }
+  const float nr = (float)n * b.r;
+  if (nr <= URSM_BINOM_INV_MAX) {
+    b.s = URSM_DIV(b.r, b.rc);
+    b.c = (float)(n + 1) * b.s;
+    const int guard = (int)(nr + 10.0f * sqrtf(nr * b.rc + 1.0f));
+    b.bound = guard < n ? guard : n;
+    binom_inv_start(b, u);
+  } else {
+    b.mode = kBinBtrs;
+  }
+}
+
+// up to `steps` CDF steps; kBinDone when u falls inside the current atom, kBinRetry
+// when the search ran past the guard bound (rounding deficit of the fp32 pmf sum).
+// pmf(x)/pmf(x-1) = (n-x+1) s / x = c/x - s.
+URSM_HD void binom_inv_steps(BinomState& b, int steps) {
+  for (int it = 0; it < steps; ++it) {
+    if (b.mode != kBinInv) break;
+    if (b.u <= b.px) {
+      b.result = b.flip ? b.n - b.x : b.x;
+      b.mode = kBinDone;
+      break;
+    }
+    b.u -= b.px;
+    ++b.x;
+    if (b.x > b.bound) {
+      b.mode = kBinRetry;
+      break;
+    }
+    b.px *= fmaf(b.c, URSM_DIV(1.0f, (float)b.x), -b.s);
+  }
+}
+
+URSM_HD double btrs_fc(int k) {  // Stirling series tail log(k!) - [Stirling approximation]
+  switch (k) {
+    case 0: return 0.08106146679532726;
+    case 1: return 0.04134069595540929;
+    case 2: return 0.02767792568499834;
+    case 3: return 0.02079067210376509;
+    case 4: return 0.01664469118982119;
+    case 5: return 0.01387612882307075;
+    case 6: return 0.01189670994589177;
+    case 7: return 0.01041126526197209;
+    case 8: return 0.009255462182712733;
+    case 9: return 0.008330563433362871;
+  }
+  const double kp1 = k + 1.0, kp1sq = kp1 * kp1;
+  return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / kp1;
+}
+
+// one BTRS attempt from two uniforms; kBinDone on acceptance
+URSM_HD void binom_btrs_attempt(BinomState& b, float U, float V) {
+  const float n = (float)b.n, r = b.r;
+  const float spq = sqrtf(n * r * b.rc);
+  const float bb = 1.15f + 2.53f * spq;
+  const float aa = -0.0873f + 0.0248f * bb + 0.01f * r;
+  const float c = n * r + 0.5f;
+  const float vr = 0.92f - 4.2f / bb;
+  const float u = U - 0.5f;
+  const float us = 0.5f - fabsf(u);
+  const float kf = floorf((2.0f * aa / us + bb) * u + c);
+  if (!(kf >= 0.0f && kf <= n)) return;
+  const int k = (int)kf;
+  bool ok = (us >= 0.07f && V <= vr);
+  if (!ok) {
+    const double alpha = (2.83 + 5.1 / (double)bb) * (double)spq;
+    const double usd = us;
+    const double lhs = log((double)V * alpha / ((double)aa / (usd * usd) + (double)bb));
+    const double rd = (double)r / (double)b.rc;  // odds
+    const int m = (int)floor(((double)b.n + 1.0) * (double)r);
+    const double nd = b.n;
+    const double rhs = (m + 0.5) * log((m + 1.0) / (rd * (nd - m + 1.0))) +
+                       (nd + 1.0) * log((nd - m + 1.0) / (nd - k + 1.0)) +
+                       (k + 0.5) * log(rd * (nd - k + 1.0) / (k + 1.0)) + btrs_fc(m) +
+                       btrs_fc(b.n - m) - btrs_fc(k) - btrs_fc(b.n - k);
+    ok = lhs <= rhs;
+  }
+  if (ok) {
+    b.result = b.flip ? b.n - k : k;
+    b.mode = kBinDone;
+  }
+}
+
+// run the state machine to completion (host tests; same arithmetic as the kernel)
+template <class RNG>
+URSM_HD int binomial_f32(int n, float p, float pc, RNG& rng) {
+  BinomState b;
+  binom_begin(b, n, p, pc, rng.uniform());
+  for (int guard = 0; guard < 100000 && b.mode != kBinDone; ++guard) {
+    if (b.mode == kBinInv) {
+      binom_inv_steps(b, 8);
+    } else if (b.mode == kBinBtrs) {
+      const float U = rng.uniform(), V = rng.uniform();
+      binom_btrs_attempt(b, U, V);
+    } else {  // kBinRetry
+      binom_inv_start(b, rng.uniform());
+    }
+  }
+  return b.result;
 }
 
 }  // namespace ursm

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
 
     const unsigned int gl = (unsigned int)(a.cell_offset + l);  // global cell id keys the RNG
     const float Rf = (float)a.R[l];
+    const float invR = Rf > 0.f ? 1.0f / Rf : 0.f;
     const float* Acol = a.Aslot + (size_t)type * slots;
     const int i0 = tid * g;                               // first gene of this thread's run
     const int gcount = max(0, min(g, N - i0));
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
             swa += wd * ad;
             swaa += wd * ad * ad;
             const unsigned int Sold = (f >> 1) & 1u, pos = f & 1u;
-            const float Tth = s_threshold(psi, u01(rS), av, Rf);
+            const float Tth = s_threshold(psi, u01(rS), av, Rf, invR);
             unsigned int Snew = 1u;
             if (!pos) {
               const double so = s_run - (Sold ? ad : 0.0);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
               philox_block(a.key, (uint32_t)i, gl, ctr2, 0u, r0, r1, r2, r3);
               const float u = u01(r3);
               const float psi = fmaf(ft, av, fk);
-              const float Tth = s_threshold(psi, u, av, Rf);
+              const float Tth = s_threshold(psi, u, av, Rf, invR);
               const double so = s_run - (Sold ? ad : 0.0);
               Snew = (so > (double)Tth) ? 1u : 0u;
               margin = fminf(margin, fabsf((float)(so - (double)Tth)));

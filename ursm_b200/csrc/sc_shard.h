@@ -39,6 +39,8 @@ struct BkShard {
   long long sample_offset = 0;
   DevBuf<float> Xown;
   const float* X = nullptr;      // [M][N] counts
+  DevBuf<float> Xs;              // [M][N] columns sorted by total count (Gibbs split kernel)
+  DevBuf<int> perm;              // [N] sorted position -> gene
   DevBuf<double> A;              // [K][N] type-major fp64
   DevBuf<double> alpha;          // [K]
   DevBuf<double> W;              // [M][K] (sample-major)
