@@ -75,7 +75,10 @@ def test_bulk_split_moments_frozen_W(golden):
     z2 = _zscores(bk.suff_stats["exp_Zjk"], EZ.sum(axis=1), np.sqrt(VZ.sum(axis=1) / S))
     for z in (z1, z2):
         assert np.abs(z).max() < 5.0
-        assert abs(np.mean(z * z) - 1.0) < 0.25
+        # mean of n chi^2_1 variables has sd sqrt(2/n); entries of one sample / gene are
+        # negatively correlated through the sum constraint, hence 6 "independent" sd
+        assert abs(np.mean(z * z) - 1.0) < 6.0 * np.sqrt(2.0 / z.size)
+        assert abs(np.mean(z)) < 5.0 / np.sqrt(z.size)
     # exact invariants of a multinomial split
     np.testing.assert_allclose(bk.suff_stats["exp_Zjk"].sum(axis=1), X.sum(axis=1), rtol=1e-12)
     np.testing.assert_allclose(bk.suff_stats["exp_Zik"].sum(axis=1), X.sum(axis=0), rtol=1e-12)
@@ -100,12 +103,12 @@ def test_bulk_dirichlet_moments_frozen_Z():
     EW = a / a0
     VW = a * (a0 - a) / (a0 ** 2 * (a0 + 1))
     z = _zscores(bk.suff_stats["exp_W"].T, EW, np.sqrt(VW / S))
-    assert np.abs(z).max() < 5.0 and abs(np.mean(z * z) - 1) < 0.25
+    assert np.abs(z).max() < 5.0 and abs(np.mean(z * z) - 1) < 6.0 * np.sqrt(2.0 / z.size)
     from scipy.special import polygamma
     ElogW = digamma(a) - digamma(a0)
     VlogW = polygamma(1, a) - polygamma(1, a0)
     z = _zscores(bk.suff_stats["exp_logW"].T, ElogW, np.sqrt(VlogW / S))
-    assert np.abs(z).max() < 5.0 and abs(np.mean(z * z) - 1) < 0.25
+    assert np.abs(z).max() < 5.0 and abs(np.mean(z * z) - 1) < 6.0 * np.sqrt(2.0 / z.size)
     np.testing.assert_allclose(bk.suff_stats["exp_Zjk"], n, rtol=1e-12)
 
 

@@ -124,53 +124,59 @@ __global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
 
 // ---------------------------------------------------------------------------
 // draw_Z (:132-138) for one Gibbs sweep: Z_ji. ~ Mult(X_ji, W_.j A_i. / AW_ij) as a
-// chain of K-1 conditional binomials.  A thread owns one gene and walks the CTA's
-// chunk of bulk samples; the binomials are data-dependent loops (inversion takes
-// ~n p steps, BTRS is a rejection sampler), so lanes are DESYNCHRONISED: every trip of
-// the warp loop gives each lane a bounded slice of work on its own current
-// (sample, type) item -- 8 inversion steps or one BTRS attempt -- and a lane that
-// finishes an item moves on by itself (samplers.cuh::BinomState).  Z is consumed on
-// the spot: sum_i Z_jik -> shared-memory integer atomics (-> one global atomic per
-// CTA, sample, type), sum_j Z_jik -> per-thread shared-memory counters, flushed once.
-// Arithmetic is fp32 on ratios of positive suffix sums (no cancellation); counts are
-// exact integers.
+// chain of K-1 conditional binomials.  The binomials are data-dependent loops
+// (inversion takes ~n p steps, BTRS is a rejection sampler whose exact test is ~10x the
+// cost of its squeeze), so the work is scheduled dynamically INSIDE each warp:
+//   * a warp owns 32 genes x the CTA's chunk of bulk samples = a queue of entries;
+//     a lane that finishes an entry takes the next one (ballot + popc, no atomics);
+//   * every trip of the warp loop gives each lane a bounded slice of work on its own
+//     current (entry, type) item -- 8 inversion steps or one BTRS attempt
+//     (samplers.cuh::BinomState).
+// X is stored with its columns sorted by total count, so the 32 genes of a warp have
+// similar depth.  Z is consumed on the spot: sum_i Z_jik and sum_j Z_jik go to
+// shared-memory integer counters (flushed once per CTA).  Arithmetic is fp32 on
+// ratios of positive suffix sums (no cancellation); counts are exact integers; the
+// RNG is keyed on the ORIGINAL gene id and the global sample id, so results depend
+// neither on the sort nor on the sharding.
 // ---------------------------------------------------------------------------
 constexpr int kSplitThreads = 256;
 
 __global__ void __launch_bounds__(kSplitThreads) bk_split_kernel(BkTileArgs a) {
   extern __shared__ __align__(16) unsigned char split_smem[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
   const int K = a.K, N = a.N;
   const long long j0 = (long long)blockIdx.y * a.chunk;
   const long long j1 = min(a.M, j0 + a.chunk);
   const int nloc = (int)(j1 - j0);
   float* Wsm = reinterpret_cast<float*>(split_smem);                      // [chunk][K]
   unsigned int* Jsm = reinterpret_cast<unsigned int*>(Wsm + a.chunk * K);  // [chunk][K]
-  float* As = reinterpret_cast<float*>(Jsm + a.chunk * K);                 // [K][T]
-  float* suf = As + K * kSplitThreads;                                     // [K+1][T]
+  float* As = reinterpret_cast<float*>(Jsm + a.chunk * K);                 // [K][T] by gene slot
+  float* suf = As + K * kSplitThreads;                                     // [K+1][T] by thread
   unsigned int* accI = reinterpret_cast<unsigned int*>(suf + (K + 1) * kSplitThreads);  // [K][T]
+  int* gene_of = reinterpret_cast<int*>(accI + K * kSplitThreads);         // [T] original gene id
   for (int t = tid; t < nloc * K; t += kSplitThreads) {
     Wsm[t] = (float)a.W[j0 * K + t];
     Jsm[t] = 0u;
   }
-  // X is stored with its columns sorted by total count, so the lanes of a warp hold
-  // genes of similar depth and their data-dependent binomial loops take similar time;
-  // `gene` is the original index (it keys the RNG: results do not depend on the sort)
-  const int gi = blockIdx.x * kSplitThreads + tid;
-  const bool in = gi < N;
-  const int gene = in ? a.perm[gi] : 0;
-  for (int k = 0; k < K; ++k) {
-    As[k * kSplitThreads + tid] = in ? (float)a.A[(size_t)k * N + gene] : 0.f;
-    accI[k * kSplitThreads + tid] = 0u;
+  {
+    const int gi = blockIdx.x * kSplitThreads + tid;
+    const bool in = gi < N;
+    const int gene = in ? a.perm[gi] : -1;
+    gene_of[tid] = gene;
+    for (int k = 0; k < K; ++k) {
+      As[k * kSplitThreads + tid] = in ? (float)a.A[(size_t)k * N + gene] : 0.f;
+      accI[k * kSplitThreads + tid] = 0u;
+    }
+    suf[K * kSplitThreads + tid] = 0.f;
   }
-  suf[K * kSplitThreads + tid] = 0.f;
   __syncthreads();
 
-  // per-lane state
-  int jl = in ? 0 : nloc;  // current sample (local)
-  int k = 0, rem = 0, nw = 0;
-  bool fresh = true;       // need to open the entry (jl, gi)
-  bool item = false;       // a binomial is in flight
+  const int gwarp = blockIdx.x * kSplitThreads + wbase;  // first sorted gene of this warp
+  const int total = (gwarp < N) ? 32 * nloc : 0;          // entries in the warp's queue
+  int cursor = 0;                                         // warp-uniform
+  bool need = true, active = false;
+  int jl = 0, slot = 0, gene = 0, k = 0, rem = 0, nw = 0;
+  bool item = false;
   uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
   BinomState b;
   b.mode = kBinDone;
@@ -186,77 +192,91 @@ __global__ void __launch_bounds__(kSplitThreads) bk_split_kernel(BkTileArgs a) {
     return u01(w);
   };
 
-  while (__any_sync(0xffffffffu, jl < nloc)) {
-    if (jl < nloc) {
-      if (fresh) {
-        const float xf = a.X[(size_t)(j0 + jl) * N + gi];
-        if (xf == 0.f) {  // nothing to split
-          ++jl;
+  while (true) {
+    // ---- hand the next entries of the queue to the lanes that are free
+    const unsigned int free_mask = __ballot_sync(0xffffffffu, need);
+    if (need) {
+      const int e = cursor + __popc(free_mask & ((1u << lane) - 1u));
+      need = false;
+      if (e < total) {
+        jl = e >> 5;
+        slot = wbase + (e & 31);
+        gene = gene_of[slot];
+        const float xf = (gene >= 0) ? a.X[(size_t)(j0 + jl) * N + gwarp + (e & 31)] : 0.f;
+        if (xf == 0.f) {
+          need = true;  // nothing to split: take another entry next trip
         } else {
           rem = (int)xf;
           const float* Wj = Wsm + jl * K;
           float acc = 0.f;
           for (int kk = K - 1; kk >= 0; --kk) {  // suffix sums of W_kj A_ik (all positive)
-            acc += Wj[kk] * As[kk * kSplitThreads + tid];
+            acc += Wj[kk] * As[kk * kSplitThreads + slot];
             suf[kk * kSplitThreads + tid] = acc;
           }
           k = 0;
           nw = 0;
-          fresh = false;
           item = false;
+          active = true;
         }
       }
-      if (!fresh) {
-        if (!item) {
-          if (k == K - 1 || rem == 0) {
-            // the last type takes what is left (also closes an exhausted entry)
-            if (rem > 0) {
-              atomicAdd(&Jsm[jl * K + k], (unsigned int)rem);
-              accI[k * kSplitThreads + tid] += (unsigned int)rem;
-            }
-            ++jl;
-            fresh = true;
-          } else {
-            const float sk = suf[k * kSplitThreads + tid];
-            const float sn = suf[(k + 1) * kSplitThreads + tid];
-            const float pc = sn / sk;                       // P(not type k | not yet assigned)
-            const float pk = (sk - sn) / sk;
-            // W_kj A_ik / suffix, formed from the product itself when it is the small side
-            const float qk = Wsm[jl * K + k] * As[k * kSplitThreads + tid];
-            binom_begin(b, rem, (pk < 0.5f) ? qk / sk : pk, pc, next_uniform());
-            item = true;
-          }
+    }
+    cursor += __popc(free_mask);
+    if (!__any_sync(0xffffffffu, active || need)) break;
+    // ---- (A) open the next (entry, type) item
+    if (active && !item) {
+      if (k == K - 1 || rem == 0) {
+        // the last type takes what is left (also closes an exhausted entry)
+        if (rem > 0) {
+          atomicAdd(&Jsm[jl * K + k], (unsigned int)rem);
+          atomicAdd(&accI[k * kSplitThreads + slot], (unsigned int)rem);
         }
-        if (item) {
-          if (b.mode == kBinInv) {
-            binom_inv_steps(b, 8);
-          } else if (b.mode == kBinBtrs) {
-            const float U = next_uniform(), V = next_uniform();
-            binom_btrs_attempt(b, U, V);
-          } else if (b.mode == kBinRetry) {
-            binom_inv_start(b, next_uniform());
-          }
-          if (b.mode == kBinDone) {
-            const int z = b.result;
-            if (z > 0) {
-              atomicAdd(&Jsm[jl * K + k], (unsigned int)z);
-              accI[k * kSplitThreads + tid] += (unsigned int)z;
-              rem -= z;
-            }
-            ++k;
-            item = false;
-          }
+        active = false;
+        need = true;
+      } else {
+        const float sk = suf[k * kSplitThreads + tid];
+        const float sn = suf[(k + 1) * kSplitThreads + tid];
+        const float inv = URSM_DIV(1.0f, sk);
+        const float pc = sn * inv;  // P(not type k | not yet assigned)
+        // W_kj A_ik / suffix, formed from the product itself when it is the small side
+        const float qk = Wsm[jl * K + k] * As[k * kSplitThreads + slot];
+        const float pk = (sk - sn) * inv;
+        binom_begin(b, rem, (pk < 0.5f) ? qk * inv : pk, pc, next_uniform());
+        item = true;
+      }
+    }
+    // ---- (B) inversion: up to 8 CDF steps, ended early by a warp vote
+    for (int it = 0; it < 8; ++it) {
+      const bool stepping = active && item && b.mode == kBinInv;
+      if (!__any_sync(0xffffffffu, stepping)) break;
+      if (stepping) binom_inv_step(b);
+    }
+    // ---- (C) one BTRS attempt / restart of a failed inversion / commit
+    if (active && item) {
+      if (b.mode == kBinBtrs) {
+        const float U = next_uniform(), V = next_uniform();
+        binom_btrs_attempt(b, U, V);
+      } else if (b.mode == kBinRetry) {
+        binom_inv_start(b, next_uniform());
+      }
+      if (b.mode == kBinDone) {
+        const int z = b.result;
+        if (z > 0) {
+          atomicAdd(&Jsm[jl * K + k], (unsigned int)z);
+          atomicAdd(&accI[k * kSplitThreads + slot], (unsigned int)z);
+          rem -= z;
         }
+        ++k;
+        item = false;
       }
     }
   }
   __syncthreads();
   for (int t = tid; t < nloc * K; t += kSplitThreads)
     if (Jsm[t] != 0u) atomicAdd(&a.sumJ[j0 * K + t], (double)Jsm[t]);
-  if (in && a.accumulate_I) {
+  if (gene_of[tid] >= 0 && a.accumulate_I) {
     for (int kk = 0; kk < K; ++kk) {
       const unsigned int v = accI[kk * kSplitThreads + tid];
-      if (v != 0u) atomicAdd(&a.sumI[(size_t)kk * N + gene], (double)v * a.scaleI);
+      if (v != 0u) atomicAdd(&a.sumI[(size_t)kk * N + gene_of[tid]], (double)v * a.scaleI);
     }
   }
 }
@@ -272,7 +292,7 @@ static void bk_launch_split(BkShard* b, BkTileArgs& a, cudaStream_t st) {
   a.sample_offset = b->sample_offset;
   const int K = b->K;
   const int gx = (b->N + kSplitThreads - 1) / kSplitThreads;
-  const size_t per_thread = (size_t)(3 * K + 1) * kSplitThreads * 4;
+  const size_t per_thread = (size_t)(3 * K + 2) * kSplitThreads * 4;
   // a chunk's W rows and per-sample sums (8 B per sample and type) share the CTA's smem
   const long long max_chunk = std::max<long long>(1, (long long)(24 * 1024) / (8 * (long long)K));
   long long want_y = std::max<long long>(1, (long long)(4 * b->num_sms + gx - 1) / gx);

@@ -337,8 +337,8 @@ URSM_HD int binomial(int n, double p, RNG& rng) {
 // Binomial(n, p) as a resumable state machine in fp32 for the bulk split kernel
 // (csrc/bk_gibbs.cu::bk_split_kernel): lanes of a warp interleave "a few inversion
 // steps" / "one BTRS attempt" instead of each running its own data-dependent loop.
-//   n r <= 14  sequential inversion from 0 (as binomial_inversion above), fp32;
-//   n r  > 14  BTRS, Hormann's transformed rejection with squeeze (1993): the
+//   n r <= 40  sequential inversion from 0 (as binomial_inversion above), fp32;
+//   n r  > 40  BTRS, Hormann's transformed rejection with squeeze (1993): the
 //              86% quick-accept path in fp32, the exact log-ratio test in fp64.
 // `p` and its complement are passed separately (both are ratios of positive sums in
 // the caller), so 1 - p is never formed by subtraction.
@@ -351,11 +351,12 @@ struct BinomState {
   bool flip;
 };
 
-// n r above which BTRS replaces inversion (BTRS needs n r >= 10)
-#define URSM_BINOM_INV_MAX 14.0f
+// n r above which BTRS replaces inversion (BTRS needs n r >= 10; pmf(0) >= e^-56 stays a
+// normal fp32 number up to here)
+#define URSM_BINOM_INV_MAX 40.0f
 
 URSM_HD void binom_inv_start(BinomState& b, float u) {
-  // pmf(0) = (1-r)^n; n r <= 14 keeps it above 1e-7
+  // pmf(0) = (1-r)^n
   b.px = URSM_EXPF((float)b.n * log1pf(-b.r));
   b.x = 0;
   b.u = u;
@@ -406,21 +407,39 @@ URSM_HD void binom_inv_steps(BinomState& b, int steps) {
   }
 }
 
-URSM_HD double btrs_fc(int k) {  // Stirling series tail log(k!) - [Stirling approximation]
-  switch (k) {
-    case 0: return 0.08106146679532726;
-    case 1: return 0.04134069595540929;
-    case 2: return 0.02767792568499834;
-    case 3: return 0.02079067210376509;
-    case 4: return 0.01664469118982119;
-    case 5: return 0.01387612882307075;
-    case 6: return 0.01189670994589177;
-    case 7: return 0.01041126526197209;
-    case 8: return 0.009255462182712733;
-    case 9: return 0.008330563433362871;
+// a single CDF step (the kernel drives these with a warp vote so a chunk ends as soon
+// as every lane of the warp has landed)
+URSM_HD void binom_inv_step(BinomState& b) {
+  if (b.u <= b.px) {
+    b.result = b.flip ? b.n - b.x : b.x;
+    b.mode = kBinDone;
+    return;
   }
-  const double kp1 = k + 1.0, kp1sq = kp1 * kp1;
-  return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / kp1;
+  b.u -= b.px;
+  ++b.x;
+  if (b.x > b.bound) {
+    b.mode = kBinRetry;
+    return;
+  }
+  b.px *= fmaf(b.c, URSM_DIV(1.0f, (float)b.x), -b.s);
+}
+
+URSM_HD float btrs_fc(int k) {  // Stirling series tail: log(k!) - Stirling's formula
+  switch (k) {
+    case 0: return 0.08106146679532726f;
+    case 1: return 0.04134069595540929f;
+    case 2: return 0.02767792568499834f;
+    case 3: return 0.02079067210376509f;
+    case 4: return 0.01664469118982119f;
+    case 5: return 0.01387612882307075f;
+    case 6: return 0.01189670994589177f;
+    case 7: return 0.01041126526197209f;
+    case 8: return 0.009255462182712733f;
+    case 9: return 0.008330563433362871f;
+  }
+  // values <= 0.0076: fp32 keeps them to 1e-9 absolute, far below the test's resolution
+  const float ik = URSM_DIV(1.0f, (float)k + 1.0f), ik2 = ik * ik;
+  return (1.0f / 12 - (1.0f / 360 - 1.0f / 1260 * ik2) * ik2) * ik;
 }
 
 // one BTRS attempt from two uniforms; kBinDone on acceptance
@@ -438,17 +457,32 @@ URSM_HD void binom_btrs_attempt(BinomState& b, float U, float V) {
   const int k = (int)kf;
   bool ok = (us >= 0.07f && V <= vr);
   if (!ok) {
-    const double alpha = (2.83 + 5.1 / (double)bb) * (double)spq;
-    const double usd = us;
-    const double lhs = log((double)V * alpha / ((double)aa / (usd * usd) + (double)bb));
-    const double rd = (double)r / (double)b.rc;  // odds
-    const int m = (int)floor(((double)b.n + 1.0) * (double)r);
-    const double nd = b.n;
-    const double rhs = (m + 0.5) * log((m + 1.0) / (rd * (nd - m + 1.0))) +
-                       (nd + 1.0) * log((nd - m + 1.0) / (nd - k + 1.0)) +
-                       (k + 0.5) * log(rd * (nd - k + 1.0) / (k + 1.0)) + btrs_fc(m) +
-                       btrs_fc(b.n - m) - btrs_fc(k) - btrs_fc(b.n - k);
-    ok = lhs <= rhs;
+    // exact test: V alpha / (a/us^2 + b) <= f(k)/f(m), m = mode
+    const float alpha = (2.83f + URSM_DIV(5.1f, bb)) * spq;
+    const float lhs = URSM_DIV(V * alpha, URSM_DIV(aa, us * us) + bb);
+    const int m = (int)floorf((n + 1.0f) * r);
+    const int d = k - m;
+    if (d >= -32 && d <= 32) {
+      // f(k)/f(m) as an explicit product of at most 32 ratios (fp32, as BTPE does near
+      // the mode): f(i)/f(i-1) = (n-i+1)/i * r/(1-r)
+      const float odds = URSM_DIV(r, b.rc);
+      float F = 1.0f;
+      if (d > 0) {
+        for (int i = m + 1; i <= k; ++i) F *= URSM_DIV((float)(b.n - i + 1) * odds, (float)i);
+      } else {
+        for (int i = k + 1; i <= m; ++i) F *= URSM_DIV((float)i, (float)(b.n - i + 1) * odds);
+      }
+      ok = lhs <= F;
+    } else {
+      // far from the mode: Stirling form of log f(k)/f(m), in fp64
+      const double rd = (double)r / (double)b.rc;  // odds
+      const double nd = b.n;
+      const double rhs = (m + 0.5) * log((m + 1.0) / (rd * (nd - m + 1.0))) +
+                         (nd + 1.0) * log((nd - m + 1.0) / (nd - k + 1.0)) +
+                         (k + 0.5) * log(rd * (nd - k + 1.0) / (k + 1.0)) +
+                         (double)(btrs_fc(m) + btrs_fc(b.n - m) - btrs_fc(k) - btrs_fc(b.n - k));
+      ok = log((double)lhs) <= rhs;
+    }
   }
   if (ok) {
     b.result = b.flip ? b.n - k : k;
