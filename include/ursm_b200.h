@@ -131,10 +131,18 @@ int ursm_bk_kernel_ms(ursm_bk* bk, float* ms);
  *                        columns flagged active: d_part[k*N+i] = sum_{l in k} E[S_li] R_l/u_l,
  *                        d_part[K*N] = sum_l R_l log u_l   (length K*N+1)
  * ursm_mle_set_coeffs   installs the (all-reduced) coefficient matrices, all K x N type-major
- * ursm_mle_step_A       one outer iteration of opt_Ak :157-182 for every active column at
- *                        once: backtracking :209-233 with simplex_proj (utils.py:8-31) as the
- *                        projection, get_grad_A :262-272, get_obj_A :275-287.  d_cconst_part is
- *                        the all-reduced output of ursm_mle_pass_u.  h_delta[k] = ||dA_k||_1.
+ * ursm_mle_opt_begin/step/pass/merge/poll   opt_A_u :128-154 for every column that has cells,
+ *                        all columns at once and without a host round trip per iteration:
+ *     begin  arms the per-column loop state of opt_Ak :157-182 (active flag, iteration count)
+ *     step   backtracking :209-233 -- kCand = 16 trial step sizes init_step/2^c of every active
+ *            column are projected (simplex_proj, utils.py:8-31) and tested CONCURRENTLY, then
+ *            the first passing one is committed: the step the reference's sequential halving
+ *            loop accepts; get_grad_A :262-272, get_obj_A :275-287.  d_cconst_part is the
+ *            all-reduced output of the previous pass.
+ *     pass   opt_u :108-115 + update_gd_coeffConst :118-125 for the stepped columns -> d_part_local
+ *            (the caller all-reduces it across ranks)
+ *     merge  installs the reduced partials of the stepped columns, advances the loop state
+ *     poll   device -> host: which columns are still iterating, iteration / halving counts
  * ursm_mle_closed_form  the bulk-only column rule :149-153
  * ursm_mle_elbo_terms   the A-dependent sums of compute_elbo :290-320
  */
@@ -146,8 +154,13 @@ int ursm_mle_begin(ursm_mle* m, double* d_part, void* stream);
 int ursm_mle_pass_u(ursm_mle* m, const int32_t* h_active, double* d_part, void* stream);
 int ursm_mle_set_coeffs(ursm_mle* m, const double* d_cAinv, const double* d_cA,
                         const double* d_coeffA);
-int ursm_mle_step_A(ursm_mle* m, const int32_t* h_active, const double* d_cconst_part,
-                    double init_step, double* h_delta, int32_t* h_halvings, void* stream);
+int ursm_mle_opt_begin(ursm_mle* m, const int32_t* h_active, double init_step, double conv,
+                       int32_t maxiter, void* stream);
+int ursm_mle_opt_step(ursm_mle* m, const double* d_cconst_part, void* stream);
+int ursm_mle_opt_pass(ursm_mle* m, double* d_part_local, void* stream);
+int ursm_mle_opt_merge(ursm_mle* m, const double* d_part_local, double* d_part, void* stream);
+int ursm_mle_opt_poll(ursm_mle* m, int32_t* h_active, int32_t* h_niter, int32_t* h_halvings,
+                      double* h_delta, void* stream);
 int ursm_mle_closed_form(ursm_mle* m, int32_t k, const double* d_exp_Zik, void* stream);
 int ursm_mle_elbo_terms(ursm_mle* m, const double* d_cconst_part, double* h_terms3,
                         void* stream);

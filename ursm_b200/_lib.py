@@ -54,7 +54,11 @@ SIGNATURES = {
     "ursm_mle_begin": (c_int, [c_vp, c_vp, c_vp]),
     "ursm_mle_pass_u": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_set_coeffs": (c_int, [c_vp, c_vp, c_vp, c_vp]),
-    "ursm_mle_step_A": (c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp]),
+    "ursm_mle_opt_begin": (c_int, [c_vp, c_vp, c_dbl, c_dbl, c_i32, c_vp]),
+    "ursm_mle_opt_step": (c_int, [c_vp, c_vp, c_vp]),
+    "ursm_mle_opt_pass": (c_int, [c_vp, c_vp, c_vp]),
+    "ursm_mle_opt_merge": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "ursm_mle_opt_poll": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_closed_form": (c_int, [c_vp, c_i32, c_vp, c_vp]),
     "ursm_mle_elbo_terms": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_get_u": (c_int, [c_vp, c_vp]),

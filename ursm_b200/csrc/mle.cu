@@ -29,49 +29,79 @@ struct Mle {
   const double* cAinv = nullptr;         // [K][N] caller-owned (all-reduced)
   const double* cA = nullptr;
   const double* coeffA = nullptr;
-  DevBuf<double> u;                      // [L]
-  DevBuf<int> active, list;              // [K]
-  DevBuf<double> out;                    // [K][4]
+  DevBuf<double> u, ratio;               // [L] u_l and R_l / u_l
+  DevBuf<int> act_cur, act_next;         // [K] columns in opt_Ak at the start / end of an iteration
+  DevBuf<int> niter, base, halv;         // [K] outer iterations, halvings already tried, total halvings
+  DevBuf<double> cand;                   // [K][kCand][N] candidate columns of one backtracking batch
+  DevBuf<double> cres;                   // [K][kCand][4]: accepted?, objective, ||dA||_1, step
+  DevBuf<double> delta;                  // [K] last accepted ||dA_k||_1
   DevBuf<double> terms;                  // [4]
+  double init_step = 0, conv = 0;
+  int maxiter = 0;
   int num_sms = 148;
 };
+
+constexpr int kCand = 16;  // trial step sizes of backtracking evaluated concurrently
 
 constexpr int kColThreads = 256;
 
 // MODE 0: out[type][i] += Y_li * E[S_li]            (m_step.py:88-89)
 // MODE 1: out[type][i] += E[S_li] * R_l / u_l       (m_step.py:123-125), active types only
+// A thread owns two adjacent genes and walks a chunk of the type-sorted cells; the
+// counters are read as one 32-bit word per cell (coalesced), `ratio` = R_l/u_l comes
+// from mle_u_kernel.
 template <int MODE>
 __global__ void __launch_bounds__(kColThreads)
 mle_colsum_kernel(const float* Y, const unsigned short* cnt, const int* G, const int* order,
-                  const double* R, const double* u, const int* active, long long L, int N,
-                  int chunk, double inv_sample, double* out) {
-  const int i = blockIdx.x * kColThreads + threadIdx.x;
+                  const double* ratio, const int* active, long long L, int N, int chunk,
+                  double inv_sample, double* out) {
+  const int i = 2 * (blockIdx.x * kColThreads + threadIdx.x);
   const long long c0 = (long long)blockIdx.y * chunk, c1 = min(L, c0 + chunk);
   if (i >= N) return;
-  double acc = 0.0;
+  const bool pair = (i + 1 < N) && ((N & 1) == 0);  // 32-bit loads need even row strides
+  double acc0 = 0.0, acc1 = 0.0;
   int cur = -1;
   for (long long c = c0; c < c1; ++c) {
     const int l = order[c];
     const int type = G[l];
     if (type != cur) {
-      if (cur >= 0 && acc != 0.0) atomicAdd(&out[(size_t)cur * N + i], acc);
-      acc = 0.0;
+      if (cur >= 0) {
+        if (acc0 != 0.0) atomicAdd(&out[(size_t)cur * N + i], acc0);
+        if (acc1 != 0.0) atomicAdd(&out[(size_t)cur * N + i + 1], acc1);
+      }
+      acc0 = acc1 = 0.0;
       cur = type;
     }
     if (MODE == 1 && !active[type]) continue;
-    const double es = (double)cnt[(size_t)l * N + i] * inv_sample;
-    if (MODE == 0)
-      acc += (double)Y[(size_t)l * N + i] * es;
-    else
-      acc += es * (R[l] / u[l]);
+    const unsigned short* row = cnt + (size_t)l * N + i;
+    unsigned int c01;
+    if (pair) {
+      c01 = *reinterpret_cast<const unsigned int*>(row);
+    } else {
+      c01 = row[0];
+      if (i + 1 < N) c01 |= (unsigned int)row[1] << 16;
+    }
+    const double e0 = (double)(c01 & 0xffffu) * inv_sample, e1 = (double)(c01 >> 16) * inv_sample;
+    if (MODE == 0) {
+      const float* y = Y + (size_t)l * N + i;
+      acc0 += (double)y[0] * e0;
+      if (i + 1 < N) acc1 += (double)y[1] * e1;
+    } else {
+      const double r = ratio[l];
+      acc0 += e0 * r;
+      acc1 += e1 * r;
+    }
   }
-  if (cur >= 0 && acc != 0.0) atomicAdd(&out[(size_t)cur * N + i], acc);
+  if (cur >= 0) {
+    if (acc0 != 0.0) atomicAdd(&out[(size_t)cur * N + i], acc0);
+    if (acc1 != 0.0 && i + 1 < N) atomicAdd(&out[(size_t)cur * N + i + 1], acc1);
+  }
 }
 
-// u_l = sum_i A[i, G_l] E[S_li]  (one warp per cell; active types only)
+// u_l = sum_i A[i, G_l] E[S_li] and ratio_l = R_l / u_l  (one warp per cell; active types)
 __global__ void mle_u_kernel(const unsigned short* cnt, const int* G, const double* A,
-                             const int* active, long long L, int N, double inv_sample,
-                             double* u) {
+                             const double* R, const int* active, long long L, int N,
+                             double inv_sample, double* u, double* ratio) {
   const long long l = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (l >= L) return;
@@ -80,9 +110,23 @@ __global__ void mle_u_kernel(const unsigned short* cnt, const int* G, const doub
   const double* Ak = A + (size_t)type * N;
   const unsigned short* row = cnt + (size_t)l * N;
   double s = 0.0;
-  for (int i = lane; i < N; i += 32) s += Ak[i] * (double)row[i];
+  if ((N & 3) == 0) {  // 64-bit loads: four counters per lane and trip
+    const uint2* row4 = reinterpret_cast<const uint2*>(row);
+    for (int q = lane; q < (N >> 2); q += 32) {
+      const uint2 c = row4[q];
+      const double* a4 = Ak + 4 * q;
+      s += a4[0] * (double)(c.x & 0xffffu) + a4[1] * (double)(c.x >> 16) +
+           a4[2] * (double)(c.y & 0xffffu) + a4[3] * (double)(c.y >> 16);
+    }
+  } else {
+    for (int i = lane; i < N; i += 32) s += Ak[i] * (double)row[i];
+  }
   s = warp_sum(s);
-  if (lane == 0) u[l] = s * inv_sample;
+  if (lane == 0) {
+    const double ul = s * inv_sample;
+    u[l] = ul;
+    ratio[l] = R[l] / ul;
+  }
 }
 
 // out[type] = sum_{l in type} R_l log u_l   (compute_elbo :308), every type
@@ -136,85 +180,144 @@ __device__ double proj_lambda(const double* y, int N, double m, double* red) {
 }
 
 struct StepArgs {
-  double* A;          // [K][N] in/out
-  double* Anew;       // [K][N] scratch
-  double* y;          // [K][N] scratch
-  double* grad;       // [K][N] scratch
+  const double* A;     // [K][N] current columns
+  double* cand;        // [K][kCand][N] out: projected trial columns
+  double* cres;        // [K][kCand][4]
   const double* cAinv;
   const double* cA;
   const double* coeffA;
   const double* part;  // all-reduced sum_{l in k} E[S] R/u
-  const int* list;     // active columns
+  const int* act;      // [K]
+  const int* base;     // [K] halvings already rejected in earlier batches
   int N;
   double min_A, init_step;
-  double* out;         // [K][4]: ||dA||_1, halvings, obj_new, step
 };
 
-// One outer iteration of opt_Ak (:157-182) for one column per CTA.
-__global__ void __launch_bounds__(1024) mle_step_kernel(StepArgs a) {
-  __shared__ double red[96];
-  const int k = a.list[blockIdx.x], N = a.N, tid = threadIdx.x, T = blockDim.x;
-  double* Ak = a.A + (size_t)k * N;
-  double* An = a.Anew + (size_t)k * N;
-  double* y = a.y + (size_t)k * N;
-  double* gr = a.grad + (size_t)k * N;
+__device__ __forceinline__ void block_sum6(double* v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) v[q] = warp_sum(v[q]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) red[q * 32 + warp] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 6; ++q) v[q] = warp_sum((lane < nw) ? red[q * 32 + lane] : 0.0);
+}
+
+// One trial of backtracking (:209-233) per CTA: column blockIdx.y, step size
+// init_step / 2^(base + blockIdx.x).  The reference halves sequentially until the
+// sufficient-decrease test passes; the kCand trials of a batch are independent, so
+// they run concurrently and mle_commit_kernel takes the FIRST one that passes -- the
+// same step the sequential loop would have accepted.
+//   grad_func = -get_grad_A (:262-272), obj_func = -get_obj_A (:275-287),
+//   projection = simplex_proj (utils.py:8-31) via proj_lambda.
+__global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
+  __shared__ double red[6 * 32];
+  const int k = blockIdx.y, c = blockIdx.x, N = a.N, tid = threadIdx.x, T = blockDim.x;
+  if (!a.act[k]) return;
+  const double* Ak = a.A + (size_t)k * N;
+  double* y = a.cand + ((size_t)k * kCand + c) * N;
   const double* ci = a.cAinv + (size_t)k * N;
   const double* ca = a.cA + (size_t)k * N;
   const double* c0 = a.coeffA + (size_t)k * N;
   const double* pt = a.part + (size_t)k * N;
   const double invN = 1.0 / N;
-  // grad_func = -get_grad_A (:262-272), obj_func = -get_obj_A (:275-287)
-  double f1 = 0.0, f2 = 0.0, f3 = 0.0;
+  const double step = ldexp(a.init_step, -(a.base[k] + c));
+  double v[6] = {0, 0, 0, 0, 0, 0};
   for (int i = tid; i < N; i += T) {
-    const double v = Ak[i], cc = c0[i] - pt[i];
-    gr[i] = -((ci[i] / v + ca[i] * v + cc) * invN);
-    f1 += ci[i] * log(v);
-    f2 += ca[i] * v * v;
-    f3 += cc * v;
+    const double x = Ak[i], cc = c0[i] - pt[i];
+    const double g = -((ci[i] / x + ca[i] * x + cc) * invN);
+    y[i] = x - step * g;
+    v[0] += ci[i] * log(x);
+    v[1] += ca[i] * x * x;
+    v[2] += cc * x;
   }
-  f1 = block_sum(f1, red);
-  f2 = block_sum(f2, red);
-  f3 = block_sum(f3, red);
-  const double obj_old = -((f1 + f2 / 2.0 + f3) * invN);
-  double step = a.init_step, obj_new = 0.0;
-  int halvings = 0;
-  for (;; ++halvings) {
-    for (int i = tid; i < N; i += T) y[i] = Ak[i] - step * gr[i];
-    __syncthreads();
-    const double lam = proj_lambda(y, N, a.min_A, red);
-    double g2 = 0.0, gg = 0.0;
-    f1 = f2 = f3 = 0.0;
-    for (int i = tid; i < N; i += T) {
-      const double nv = fmax(y[i] + lam, a.min_A);
-      const double Gt = (Ak[i] - nv) / step;
-      const double cc = c0[i] - pt[i];
-      An[i] = nv;
-      g2 += Gt * Gt;
-      gg += gr[i] * Gt;
-      f1 += ci[i] * log(nv);
-      f2 += ca[i] * nv * nv;
-      f3 += cc * nv;
-    }
-    block_sum2(g2, gg, red);
-    f1 = block_sum(f1, red);
-    f2 = block_sum(f2, red);
-    f3 = block_sum(f3, red);
-    obj_new = -((f1 + f2 / 2.0 + f3) * invN);
-    if (!(obj_new > obj_old + (step * 0.5) * g2 - step * gg) || halvings >= 1000) break;
-    step *= 0.5;
-  }
-  double d = 0.0;
+  block_sum6(v, red);
+  const double obj_old = -((v[0] + v[1] / 2.0 + v[2]) * invN);
+  __syncthreads();
+  const double lam = proj_lambda(y, N, a.min_A, red);
+  for (int q = 0; q < 6; ++q) v[q] = 0.0;
   for (int i = tid; i < N; i += T) {
-    d += fabs(An[i] - Ak[i]);
-    Ak[i] = An[i];
+    const double x = Ak[i], cc = c0[i] - pt[i];
+    const double g = -((ci[i] / x + ca[i] * x + cc) * invN);
+    const double nv = fmax(y[i] + lam, a.min_A);
+    const double Gt = (x - nv) / step;
+    y[i] = nv;
+    v[0] += ci[i] * log(nv);
+    v[1] += ca[i] * nv * nv;
+    v[2] += cc * nv;
+    v[3] += Gt * Gt;
+    v[4] += g * Gt;
+    v[5] += fabs(nv - x);
   }
-  d = block_sum(d, red);
+  block_sum6(v, red);
   if (tid == 0) {
-    a.out[k * 4 + 0] = d;
-    a.out[k * 4 + 1] = (double)halvings;
-    a.out[k * 4 + 2] = obj_new;
-    a.out[k * 4 + 3] = step;
+    const double obj_new = -((v[0] + v[1] / 2.0 + v[2]) * invN);
+    const bool halve = obj_new > obj_old + (step * 0.5) * v[3] - step * v[4];
+    double* r = a.cres + ((size_t)k * kCand + c) * 4;
+    r[0] = halve ? 0.0 : 1.0;
+    r[1] = obj_new;
+    r[2] = v[5];
+    r[3] = step;
   }
+}
+
+// Per column: accept the first passing trial of the batch (or schedule the next batch of
+// halvings), advance the opt_Ak loop state (:164-181).
+__global__ void mle_commit_kernel(double* A, const double* cand, const double* cres,
+                                  const int* act, int* act_next, int* niter, int* base, int* halv,
+                                  double* delta, int N, double conv, int maxiter) {
+  const int k = blockIdx.x;
+  if (!act[k]) {
+    if (threadIdx.x == 0) act_next[k] = 0;
+    return;
+  }
+  int win = -1;
+  for (int c = 0; c < kCand; ++c)
+    if (cres[((size_t)k * kCand + c) * 4] != 0.0) {
+      win = c;
+      break;
+    }
+  if (win < 0 && base[k] + kCand >= 1024) win = kCand - 1;  // step underflow guard
+  if (win < 0) {  // every trial of this batch was rejected: keep halving
+    if (threadIdx.x == 0) {
+      base[k] += kCand;
+      act_next[k] = 1;
+    }
+    return;
+  }
+  const double* src = cand + ((size_t)k * kCand + win) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) A[(size_t)k * N + i] = src[i];
+  if (threadIdx.x == 0) {
+    const double d = cres[((size_t)k * kCand + win) * 4 + 2];
+    delta[k] = d;
+    halv[k] += base[k] + win;
+    base[k] = 0;
+    const int n = ++niter[k];
+    act_next[k] = (d > conv && n < maxiter) ? 1 : 0;
+  }
+}
+
+// part[k][:] <- part_local[k][:] for the columns that were stepped; the per-type
+// sum_l R_l log u_l tail is refreshed for every type; then the loop state advances.
+__global__ void mle_merge_kernel(const double* part_local, double* part, const int* act, int N,
+                                 int K) {
+  const int k = blockIdx.y;
+  if (k == K) {
+    if (blockIdx.x == 0 && threadIdx.x < K)
+      part[(size_t)K * N + threadIdx.x] = part_local[(size_t)K * N + threadIdx.x];
+    return;
+  }
+  if (!act[k]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) part[(size_t)k * N + i] = part_local[(size_t)k * N + i];
+}
+
+__global__ void mle_advance_kernel(int* act_cur, const int* act_next, int K) {
+  if (threadIdx.x < K) act_cur[threadIdx.x] = act_next[threadIdx.x];
 }
 
 // A_k = simplex_proj(v / sum v)   (m_step.py:149-153, utils.py:8-31)
@@ -283,6 +386,7 @@ int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t
                     double min_A) {
   URSM_API_BEGIN
   URSM_REQUIRE(out && N > 0 && K > 0 && min_A > 0, "ursm_mle_create: bad argument");
+  URSM_REQUIRE(K <= 32, "ursm_mle_create: K <= 32 cell types supported");
   Mle* m = new Mle();
   m->sc = reinterpret_cast<ScShard*>(sc);
   m->bk = reinterpret_cast<BkShard*>(bk);
@@ -301,13 +405,22 @@ int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t
     m->Anew.alloc(KN);
     m->y.alloc(KN);
     m->grad.alloc(KN);
-    m->active.alloc(K);
-    m->list.alloc(K);
-    m->out.alloc(4 * (size_t)K);
+    m->act_cur.alloc(K);
+    m->act_next.alloc(K);
+    m->niter.alloc(K);
+    m->base.alloc(K);
+    m->halv.alloc(K);
+    m->delta.alloc(K);
+    m->act_cur.zero();
+    m->act_next.zero();
+    m->cand.alloc(KN * kCand);
+    m->cres.alloc((size_t)K * kCand * 4);
     m->terms.alloc(4);
     if (m->sc) {
       m->u.alloc(m->sc->L);
       m->u.zero();
+      m->ratio.alloc(m->sc->L);
+      m->ratio.zero();
     }
     URSM_CUDA(cudaDeviceSynchronize());
   } catch (...) {
@@ -352,40 +465,46 @@ int ursm_mle_begin(ursm_mle* mm, double* d_part, void* stream) {
   URSM_CUDA(cudaMemsetAsync(d_part, 0, (size_t)m->K * m->N * sizeof(double), st));
   if (m->sc) {
     ScShard* s = m->sc;
-    const int gx = (m->N + kColThreads - 1) / kColThreads;
+    const int gx = (m->N + 2 * kColThreads - 1) / (2 * kColThreads);
     int ny;
     const int chunk = colsum_chunk(m, s->L, gx, &ny);
     mle_colsum_kernel<0><<<dim3(gx, ny), kColThreads, 0, st>>>(
-        s->Y, s->cnt.p, s->G.p, s->order.p, s->R.p, nullptr, nullptr, s->L, m->N, chunk,
+        s->Y, s->cnt.p, s->G.p, s->order.p, nullptr, nullptr, s->L, m->N, chunk,
         1.0 / s->sample, d_part);
     URSM_LAUNCH_CHECK();
   }
   URSM_API_END
 }
 
-int ursm_mle_pass_u(ursm_mle* mm, const int32_t* h_active, double* d_part, void* stream) {
-  URSM_API_BEGIN
-  Mle* m = reinterpret_cast<Mle*>(mm);
-  URSM_REQUIRE(m && m->sc && h_active && d_part, "ursm_mle_pass_u: bad argument");
+// opt_u + update_gd_coeffConst for the columns flagged in m->act_cur (device flags)
+static void mle_pass(Mle* m, double* d_part, cudaStream_t st) {
   ScShard* s = m->sc;
-  cudaStream_t st = (cudaStream_t)stream;
   const size_t KN = (size_t)m->K * m->N;
-  URSM_CUDA(cudaMemcpyAsync(m->active.p, h_active, m->K * sizeof(int), cudaMemcpyHostToDevice, st));
   URSM_CUDA(cudaMemsetAsync(d_part, 0, (KN + m->K) * sizeof(double), st));
   const double inv = 1.0 / s->sample;
-  mle_u_kernel<<<(unsigned)((s->L + 7) / 8), 256, 0, st>>>(s->cnt.p, s->G.p, m->A.p, m->active.p,
-                                                           s->L, m->N, inv, m->u.p);
+  mle_u_kernel<<<(unsigned)((s->L + 7) / 8), 256, 0, st>>>(s->cnt.p, s->G.p, m->A.p, s->R.p,
+                                                           m->act_cur.p, s->L, m->N, inv, m->u.p,
+                                                           m->ratio.p);
   URSM_LAUNCH_CHECK();
-  const int gx = (m->N + kColThreads - 1) / kColThreads;
+  const int gx = (m->N + 2 * kColThreads - 1) / (2 * kColThreads);
   int ny;
   const int chunk = colsum_chunk(m, s->L, gx, &ny);
   mle_colsum_kernel<1><<<dim3(gx, ny), kColThreads, 0, st>>>(s->Y, s->cnt.p, s->G.p, s->order.p,
-                                                            s->R.p, m->u.p, m->active.p, s->L,
-                                                            m->N, chunk, inv, d_part);
+                                                            m->ratio.p, m->act_cur.p, s->L, m->N,
+                                                            chunk, inv, d_part);
   URSM_LAUNCH_CHECK();
   mle_rlogu_kernel<<<(unsigned)((s->L + 255) / 256), 256, 0, st>>>(s->G.p, s->R.p, m->u.p, s->L,
                                                                   d_part + KN);
   URSM_LAUNCH_CHECK();
+}
+
+int ursm_mle_pass_u(ursm_mle* mm, const int32_t* h_active, double* d_part, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && m->sc && h_active && d_part, "ursm_mle_pass_u: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  URSM_CUDA(cudaMemcpyAsync(m->act_cur.p, h_active, m->K * sizeof(int), cudaMemcpyHostToDevice, st));
+  mle_pass(m, d_part, st);
   URSM_API_END
 }
 
@@ -400,43 +519,87 @@ int ursm_mle_set_coeffs(ursm_mle* mm, const double* d_cAinv, const double* d_cA,
   URSM_API_END
 }
 
-int ursm_mle_step_A(ursm_mle* mm, const int32_t* h_active, const double* d_cconst_part,
-                    double init_step, double* h_delta, int32_t* h_halvings, void* stream) {
+int ursm_mle_opt_begin(ursm_mle* mm, const int32_t* h_active, double init_step, double conv,
+                       int32_t maxiter, void* stream) {
   URSM_API_BEGIN
   Mle* m = reinterpret_cast<Mle*>(mm);
-  URSM_REQUIRE(m && h_active && d_cconst_part && m->cAinv, "ursm_mle_step_A: bad argument");
+  URSM_REQUIRE(m && h_active && m->cAinv && init_step > 0 && maxiter >= 1,
+               "ursm_mle_opt_begin: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  std::vector<int> list;
-  for (int k = 0; k < m->K; ++k)
-    if (h_active[k]) list.push_back(k);
-  if (list.empty()) return 0;
-  URSM_CUDA(cudaMemcpyAsync(m->list.p, list.data(), list.size() * sizeof(int),
-                            cudaMemcpyHostToDevice, st));
+  m->init_step = init_step;
+  m->conv = conv;
+  m->maxiter = maxiter;
+  URSM_CUDA(cudaMemcpyAsync(m->act_cur.p, h_active, m->K * sizeof(int), cudaMemcpyHostToDevice, st));
+  URSM_CUDA(cudaMemcpyAsync(m->act_next.p, h_active, m->K * sizeof(int), cudaMemcpyHostToDevice, st));
+  m->niter.zero(st);
+  m->base.zero(st);
+  m->halv.zero(st);
+  m->delta.zero(st);
+  URSM_API_END
+}
+
+int ursm_mle_opt_step(ursm_mle* mm, const double* d_cconst_part, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && d_cconst_part && m->cAinv && m->maxiter > 0, "ursm_mle_opt_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
   StepArgs a;
   a.A = m->A.p;
-  a.Anew = m->Anew.p;
-  a.y = m->y.p;
-  a.grad = m->grad.p;
+  a.cand = m->cand.p;
+  a.cres = m->cres.p;
   a.cAinv = m->cAinv;
   a.cA = m->cA;
   a.coeffA = m->coeffA;
   a.part = d_cconst_part;
-  a.list = m->list.p;
+  a.act = m->act_cur.p;
+  a.base = m->base.p;
   a.N = m->N;
   a.min_A = m->min_A;
-  a.init_step = init_step;
-  a.out = m->out.p;
-  const int T = std::max(64, std::min(1024, (m->N + 31) / 32 * 32));
-  mle_step_kernel<<<(unsigned)list.size(), T, 0, st>>>(a);
+  a.init_step = m->init_step;
+  const int T = std::max(64, std::min(1024, (m->N / 4 + 31) / 32 * 32));
+  mle_cand_kernel<<<dim3(kCand, m->K), T, 0, st>>>(a);
   URSM_LAUNCH_CHECK();
-  std::vector<double> out(4 * (size_t)m->K);
-  URSM_CUDA(cudaMemcpyAsync(out.data(), m->out.p, out.size() * sizeof(double),
-                            cudaMemcpyDeviceToHost, st));
+  mle_commit_kernel<<<m->K, 256, 0, st>>>(m->A.p, m->cand.p, m->cres.p, m->act_cur.p,
+                                          m->act_next.p, m->niter.p, m->base.p, m->halv.p,
+                                          m->delta.p, m->N, m->conv, m->maxiter);
+  URSM_LAUNCH_CHECK();
+  URSM_API_END
+}
+
+int ursm_mle_opt_pass(ursm_mle* mm, double* d_part_local, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && m->sc && d_part_local, "ursm_mle_opt_pass: bad argument");
+  mle_pass(m, d_part_local, (cudaStream_t)stream);
+  URSM_API_END
+}
+
+int ursm_mle_opt_merge(ursm_mle* mm, const double* d_part_local, double* d_part, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && d_part_local && d_part, "ursm_mle_opt_merge: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  mle_merge_kernel<<<dim3((m->N + 255) / 256, m->K + 1), 256, 0, st>>>(d_part_local, d_part,
+                                                                       m->act_cur.p, m->N, m->K);
+  URSM_LAUNCH_CHECK();
+  mle_advance_kernel<<<1, 32, 0, st>>>(m->act_cur.p, m->act_next.p, m->K);
+  URSM_LAUNCH_CHECK();
+  URSM_API_END
+}
+
+int ursm_mle_opt_poll(ursm_mle* mm, int32_t* h_active, int32_t* h_niter, int32_t* h_halvings,
+                      double* h_delta, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && h_active, "ursm_mle_opt_poll: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t b = m->K * sizeof(int);
+  URSM_CUDA(cudaMemcpyAsync(h_active, m->act_cur.p, b, cudaMemcpyDeviceToHost, st));
+  if (h_niter) URSM_CUDA(cudaMemcpyAsync(h_niter, m->niter.p, b, cudaMemcpyDeviceToHost, st));
+  if (h_halvings) URSM_CUDA(cudaMemcpyAsync(h_halvings, m->halv.p, b, cudaMemcpyDeviceToHost, st));
+  if (h_delta)
+    URSM_CUDA(cudaMemcpyAsync(h_delta, m->delta.p, m->K * sizeof(double), cudaMemcpyDeviceToHost, st));
   URSM_CUDA(cudaStreamSynchronize(st));
-  for (int k : list) {
-    if (h_delta) h_delta[k] = out[k * 4];
-    if (h_halvings) h_halvings[k] = (int)out[k * 4 + 1];
-  }
   URSM_API_END
 }
 

@@ -80,6 +80,8 @@ class LogitNormalGEM(object):
                 lo, hi = dist.shard_bounds(self.M)
                 self._off_BK, self.M_local = lo, hi - lo
                 self.BKexpr = BKexpr[lo:hi]
+        else:
+            self.BKexpr = None
 
         self.init_para(init_A, init_pkappa, init_ptau, init_alpha)
 

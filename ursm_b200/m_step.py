@@ -95,17 +95,12 @@ class LogitNormalMLE(object):
 
     def _pass_u(self, active):
         """opt_u (:108-115) + update_gd_coeffConst (:118-125) for the active columns."""
-        import torch
         act = np.ascontiguousarray(active, dtype=np.int32)
-        _lib.call("ursm_mle_pass_u", self._h, _lib.ptr(act), self._p(self._part_local),
-                  _lib.stream_ptr())
-        dist.all_reduce_(self._part_local)  # N*K + K values per outer iteration (SURVEY 8e)
-        KN, K, N = self.K * self.N, self.K, self.N
-        idx = torch.as_tensor(np.nonzero(act)[0], device="cuda")
-        if idx.numel():
-            self._part[:KN].view(K, N)[idx] = self._part_local[:KN].view(K, N)[idx]
-        # sum_l R_l log u_l is recomputed for every type on each pass
-        self._part[KN:] = self._part_local[KN:]
+        st = _lib.stream_ptr()
+        _lib.call("ursm_mle_pass_u", self._h, _lib.ptr(act), self._p(self._part_local), st)
+        dist.all_reduce_(self._part_local)  # N*K + K values (SURVEY 8e)
+        # installs the rows of the active columns and the per-type sum_l R_l log u_l
+        _lib.call("ursm_mle_opt_merge", self._h, self._p(self._part_local), self._p(self._part), st)
 
     # -- reference API ------------------------------------------------------
     def update_suff_stats(self, suff_stats):
@@ -175,7 +170,9 @@ class LogitNormalMLE(object):
 
     def opt_A_u(self):
         """m_step.py:128-154: every column with cells runs opt_Ak (:157-182)
-        concurrently (columns are independent); the others use the closed form."""
+        concurrently (columns are independent); the others use the closed form.
+        The loop state lives on the device; the host only enqueues iterations and
+        polls the per-column flags every `poll_every` iterations."""
         if self.hasBK and self.hasSC:
             init_step = 0.01 / (self.L + self.M)
         elif self.hasBK:
@@ -193,18 +190,32 @@ class LogitNormalMLE(object):
                           _lib.stream_ptr())
                 logging.debug("\t\tOptimized A%d with closed form solution", k)
         self.niter_A[:] = 0
-        delta = np.zeros(K)
-        halv = np.zeros(K, dtype=np.int32)
-        while active.any():
-            _lib.call("ursm_mle_step_A", self._h, _lib.ptr(active), self._p(self._part),
-                      float(init_step), _lib.ptr(delta), _lib.ptr(halv), _lib.stream_ptr())
-            self._pass_u(active)
-            self.nhalvings += int(halv[active > 0].sum())
-            for k in np.nonzero(active)[0]:
-                self.niter_A[k] += 1
-                if not (delta[k] > self.MLE_CONV and self.niter_A[k] < self.MLE_maxiter):
-                    active[k] = 0
-                    logging.debug("\t\tOptimized A%d in %d iterations", k, self.niter_A[k])
+        if active.any():
+            st = _lib.stream_ptr()
+            _lib.call("ursm_mle_opt_begin", self._h, _lib.ptr(active), float(init_step),
+                      float(self.MLE_CONV), int(self.MLE_maxiter), st)
+            multi = dist.world_size() > 1
+            niter = np.zeros(K, dtype=np.int32)
+            halv = np.zeros(K, dtype=np.int32)
+            it, poll_every = 0, 8
+            while True:
+                _lib.call("ursm_mle_opt_step", self._h, self._p(self._part), st)
+                _lib.call("ursm_mle_opt_pass", self._h, self._p(self._part_local), st)
+                if multi:  # N*K + K values per outer iteration
+                    dist.all_reduce_(self._part_local)
+                _lib.call("ursm_mle_opt_merge", self._h, self._p(self._part_local),
+                          self._p(self._part), st)
+                it += 1
+                if it % poll_every == 0:
+                    _lib.call("ursm_mle_opt_poll", self._h, _lib.ptr(active), _lib.ptr(niter),
+                              _lib.ptr(halv), None, st)
+                    if not active.any():
+                        break
+            self.niter_A[:] = niter
+            self.nhalvings += int(halv.sum())
+            for k in range(K):
+                if niter[k] > 0:
+                    logging.debug("\t\tOptimized A%d in %d iterations", k, niter[k])
         self._pull_A()
         self._refresh_host_coeffs()
 
