@@ -45,11 +45,11 @@ struct ScGibbsArgs {
   const int* G;         // [L]
   const double* R;      // [L]
   const int* order;     // [L] cells sorted by type
-  const float* Aslot;   // [K][slots]
+  const float* A32;     // [K][N] fp32, gene order
   long long L;
   int N, K;
   long long cell_offset;
-  int g, slots;
+  int g, slots, pad;
   double mu_k, prec_k, mu_t, prec_t;
   int burnin, nsweeps, thin, sample;
   int sweep0;           // first sweep index (debug: run sweep `sweep0` only)
@@ -86,26 +86,39 @@ __device__ __forceinline__ double block_excl_scan(double v, double* red, double&
   return pre + inc - v;
 }
 
+// shared-memory slot of gene i: natural order with one pad word per 32 genes, so that
+// both access patterns are (nearly) conflict free -- consecutive genes (phase 1) and
+// one run of g genes per lane (phase 2)
+__device__ __forceinline__ int gslot(int i, int pad) { return i + (pad ? (i >> 5) : 0); }
+
 template <bool ACC_SMEM>
 __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
-  const int g = a.g, N = a.N, slots = a.slots;
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = a.g, N = a.N, slots = a.slots, pad = a.pad;
 
   double* red = reinterpret_cast<double*>(smem_raw);        // [32*5] reductions
   double* bc = red + 160;                                    // [4] broadcast
   int* ibc = reinterpret_cast<int*>(bc + 4);                 // [4]
-  float* w_s = reinterpret_cast<float*>(ibc + 4);            // [slots]
-  float* accA = ACC_SMEM ? (w_s + slots) : (a.scratch + (size_t)blockIdx.x * 2 * slots);
+  float* w_s = reinterpret_cast<float*>(ibc + 4);            // [slots] w of the current sweep
+  float* T_s = w_s + slots;                                  // [slots] draw_S thresholds
+  float* accA = ACC_SMEM ? (T_s + slots) : (a.scratch + (size_t)blockIdx.x * 2 * slots);
   float* accQ = accA + slots;
   unsigned short* cnt_s =
-      reinterpret_cast<unsigned short*>(ACC_SMEM ? (w_s + 3 * (size_t)slots) : (w_s + slots));
+      reinterpret_cast<unsigned short*>(ACC_SMEM ? (T_s + 3 * (size_t)slots) : (T_s + slots));
   unsigned char* fl_s = reinterpret_cast<unsigned char*>(cnt_s + slots);
 
   const double inv_sample = 1.0 / (double)a.sample;
   double* coeffA = a.stats;
   double* coeffQ = a.stats + (size_t)a.K * N;
   double* scal = a.stats + 2 * (size_t)a.K * N;
+
+  // this thread's run (phase 2) and this warp's block of genes (phase 1)
+  const int i0 = tid * g;
+  const int gcount = max(0, min(g, N - i0));
+  const int wbase = (tid & ~31) * g;
+  const int wtotal = max(0, min(32 * g, N - wbase));
+  const unsigned int lt_mask = (1u << lane) - 1u;
 
   int cur_type = -1, cells_in_acc = 0;
   for (int s = tid; s < slots; s += T) {
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     if (cur_type >= 0 && (finished || type != cur_type || cells_in_acc >= a.flush_every)) {
       // flush the CTA-private accumulators into coeffA/coeffAsq[:, cur_type]
       for (int i = tid; i < N; i += T) {
-        int slot = (i % g) * T + i / g;
+        const int slot = gslot(i, pad);
         float vA = accA[slot], vQ = accQ[slot];
         if (vA != 0.f) atomicAdd(&coeffA[(size_t)cur_type * N + i], (double)vA * inv_sample);
         if (vQ != 0.f) atomicAdd(&coeffQ[(size_t)cur_type * N + i], (double)vQ * inv_sample);
@@ -141,13 +154,11 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     const unsigned int gl = (unsigned int)(a.cell_offset + l);  // global cell id keys the RNG
     const float Rf = (float)a.R[l];
     const float invR = Rf > 0.f ? 1.0f / Rf : 0.f;
-    const float* Acol = a.Aslot + (size_t)type * slots;
-    const int i0 = tid * g;                               // first gene of this thread's run
-    const int gcount = max(0, min(g, N - i0));
+    const float* Acol = a.A32 + (size_t)type * N;  // A[:, type] in gene order
 
     // ---- init_gibbs (:212-225): S ~ Bern(1/2), S[Y>0] = 1, kappa/tau = prior means
     for (int i = tid; i < N; i += T) {
-      int slot = (i % g) * T + i / g;
+      const int slot = gslot(i, pad);
       bool pos = a.Y[(size_t)l * N + i] > 0.f;
       unsigned int S;
       if (a.S0) {
@@ -166,12 +177,8 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     double s_cur;
     {
       double part = 0.0;
-      for (int j = 0; j < g; ++j) {
-        int i = tid * g + j;
-        if (i >= N) break;
-        int slot = j * T + tid;
-        if (fl_s[slot] & 2) part += (double)Acol[slot];
-      }
+      for (int j = 0; j < gcount; ++j)
+        if (fl_s[gslot(i0 + j, pad)] & 2) part += (double)Acol[i0 + j];
       s_cur = block_sum(part, red);
     }
 
@@ -184,114 +191,110 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       const bool retained = sweep >= a.burnin && ((sweep - a.burnin) % a.thin == 0);
       const float fk = (float)kappa, ft = (float)tau;
       const float cA1 = pt, cA2 = pt * pk, cQ = -0.5f * pt * pt;
-      double sw = 0, swa = 0, swaa = 0, as = 0, s_run = s_cur;
+      const uint32_t ctr2 = kPurposeGene | (uint32_t)sweep;
+      double sw = 0, swa = 0, swaa = 0;
+      // ---- phase 1: draw_w (:318-323), the deferred update_suffStats fold and the
+      // draw_S thresholds, for the 32 g genes of this warp in ANY order.  Every trip
+      // of the loop is one sampling attempt (one Philox block, fixed work) per lane; a
+      // lane whose attempt is accepted takes the next gene of the warp's queue
+      // (ballot + popc), so neither rejections nor uneven runs leave lanes idle.
+      {
+        int cursor = 0, i = 0, slot = 0, attempt = 0;
+        bool need = true, active = false;
+        float av = 0.f, psi = 0.f;
+        uint32_t rS = 0u;
+        PgTilt pg;
+        while (true) {
+          const unsigned int free_mask = __ballot_sync(0xffffffffu, need);
+          if (need) {
+            const int e = cursor + __popc(free_mask & lt_mask);
+            need = false;
+            if (e < wtotal) {
+              i = wbase + e;
+              slot = gslot(i, pad);
+              av = Acol[i];
+              if (prev_ret) {  // update_suffStats (:245-270) of the previous sweep
+                const unsigned int Sp = (fl_s[slot] >> 1) & 1u;
+                const float wold = w_s[slot];
+                accA[slot] += ((float)Sp - 0.5f) * cA1 - wold * cA2;
+                accQ[slot] += cQ * wold;
+                cnt_s[slot] += (unsigned short)Sp;
+              }
+              psi = fmaf(ft, av, fk);
+              pg = pg_tilt(psi);
+              attempt = 0;
+              active = true;
+            }
+          }
+          cursor += __popc(free_mask);
+          if (!__any_sync(0xffffffffu, active)) break;
+          if (active) {
+            uint32_t r0, r1, r2, r3;
+            philox_block(a.key, (uint32_t)i, gl, ctr2, (uint32_t)attempt, r0, r1, r2, r3);
+            if (attempt == 0) rS = r3;  // word 3 of the first attempt: the S uniform
+            float x;
+            if (pg_attempt(pg, u01(r0), u01(r1), u01(r2), x)) {
+              const float wn = 0.25f * x;
+              w_s[slot] = wn;
+              T_s[slot] = s_threshold(psi, u01(rS), av, Rf, invR);
+              const double wd = wn, ad = av;
+              sw += wd;
+              swa += wd * ad;
+              swaa += wd * ad * ad;
+              active = false;
+              need = true;
+            } else {
+              ++attempt;
+            }
+          }
+        }
+      }
+      __syncwarp();  // phase 2 reads what other lanes of this warp wrote
+      // ---- phase 2: draw_S (:326-342), the in-cell sequential scan, kept EXACT:
+      // every thread scans its own run from the sweep-start sum (speculation), a block
+      // scan of the net changes gives the true incoming sums, threads whose incoming
+      // sum moved by more than their margin re-scan (thresholds are in shared memory,
+      // so a re-scan is three flops per zero gene), to the fixed point.
+      double as = 0, s_run = s_cur, used_in = s_cur;
       int nS = 0;
       float margin = INFINITY;
-      // ---- draw_w (:318-323) + speculative draw_S (:326-342) + deferred fold.
-      // Attempt-synchronous: every trip of the while loop is ONE sampling attempt
-      // (one Philox block, fixed work) for the lane's current gene; a lane that
-      // accepts finishes the gene and moves to the next one of its run, so the
-      // rejection sampler never leaves lanes idle inside a gene.
-      const uint32_t ctr2 = kPurposeGene | (uint32_t)sweep;
-      int j = 0, attempt = 0, slot = tid;
-      bool have = gcount > 0;
-      float av = 0.f, psi = 0.f;
-      unsigned int f = 0u;
-      uint32_t rS = 0u;
-      PgTilt pg;
-#define URSM_LOAD_GENE()                                                       \
-  do {                                                                         \
-    av = Acol[slot];                                                           \
-    f = fl_s[slot];                                                            \
-    if (prev_ret) { /* update_suffStats (:245-270) of the previous sweep */    \
-      const float wold = w_s[slot];                                            \
-      const float Sf = (float)((f >> 1) & 1u);                                 \
-      accA[slot] += (Sf - 0.5f) * cA1 - wold * cA2;                            \
-      accQ[slot] += cQ * wold;                                                 \
-      cnt_s[slot] += (unsigned short)((f >> 1) & 1u);                          \
-    }                                                                          \
-    psi = fmaf(ft, av, fk);                                                    \
-    pg = pg_tilt(psi);                                                         \
-  } while (0)
-      if (have) URSM_LOAD_GENE();
-      while (__any_sync(0xffffffffu, have)) {
-        if (have) {
-          uint32_t r0, r1, r2, r3;
-          philox_block(a.key, (uint32_t)(i0 + j), gl, ctr2, (uint32_t)attempt, r0, r1, r2, r3);
-          if (attempt == 0) rS = r3;  // word 3 of the first attempt: the S uniform
-          float x;
-          if (pg_attempt(pg, u01(r0), u01(r1), u01(r2), x)) {
-            const float wn = 0.25f * x;
-            w_s[slot] = wn;
-            const double wd = wn, ad = av;
-            sw += wd;
-            swa += wd * ad;
-            swaa += wd * ad * ad;
-            const unsigned int Sold = (f >> 1) & 1u, pos = f & 1u;
-            const float Tth = s_threshold(psi, u01(rS), av, Rf, invR);
+      bool scan = true;
+      int rounds = 0;
+      while (true) {
+        if (scan) {
+          margin = INFINITY;
+          nS = 0;
+          as = 0;
+          s_run = used_in;
+          for (int j = 0; j < gcount; ++j) {
+            const int slot = gslot(i0 + j, pad);
+            const unsigned int f = fl_s[slot];
+            // bit 1 = S of this sweep so far, bit 2 = S at the start of the sweep
+            const unsigned int pos = f & 1u;
+            const unsigned int Sold = (rounds == 0) ? ((f >> 1) & 1u) : ((f >> 2) & 1u);
+            const double ad = (double)Acol[i0 + j];
             unsigned int Snew = 1u;
             if (!pos) {
+              const double Tth = (double)T_s[slot];
               const double so = s_run - (Sold ? ad : 0.0);
-              Snew = (so > (double)Tth) ? 1u : 0u;
-              margin = fminf(margin, fabsf((float)(so - (double)Tth)));
+              Snew = (so > Tth) ? 1u : 0u;
+              margin = fminf(margin, fabsf((float)(so - Tth)));
               s_run = so + (Snew ? ad : 0.0);
             }
             fl_s[slot] = (unsigned char)(pos | (Snew << 1) | (Sold << 2));
             nS += (int)Snew;
             if (Snew) as += ad;
-            ++j;
-            slot += T;
-            attempt = 0;
-            have = j < gcount;
-            if (have) URSM_LOAD_GENE();
-          } else {
-            ++attempt;
           }
         }
-      }
-#undef URSM_LOAD_GENE
-      // ---- exact sequential semantics: fixed point over the incoming prefix sums
-      double delta = s_run - s_cur, used_in = s_cur;
-      int rounds = 0;
-      while (true) {
         double total;
+        const double delta = s_run - used_in;
         const double incoming = s_cur + block_excl_scan(delta, red, total);
         const bool viol = !(fabs(incoming - used_in) < (double)margin) && incoming != used_in &&
                           margin != INFINITY;
         if (!__syncthreads_or(viol) || rounds > T) break;
         ++rounds;
-        if (viol) {
-          s_run = incoming;
-          margin = INFINITY;
-          nS = 0;
-          as = 0;
-          for (int j = 0; j < g; ++j) {
-            const int i = tid * g + j;
-            if (i >= N) break;
-            const int slot = j * T + tid;
-            const float av = Acol[slot];
-            const double ad = av;
-            const unsigned int f = fl_s[slot];
-            const unsigned int Sold = (f >> 2) & 1u, pos = f & 1u;
-            unsigned int Snew = 1u;
-            if (!pos) {
-              uint32_t r0, r1, r2, r3;
-              philox_block(a.key, (uint32_t)i, gl, ctr2, 0u, r0, r1, r2, r3);
-              const float u = u01(r3);
-              const float psi = fmaf(ft, av, fk);
-              const float Tth = s_threshold(psi, u, av, Rf, invR);
-              const double so = s_run - (Sold ? ad : 0.0);
-              Snew = (so > (double)Tth) ? 1u : 0u;
-              margin = fminf(margin, fabsf((float)(so - (double)Tth)));
-              s_run = so + (Snew ? ad : 0.0);
-            }
-            fl_s[slot] = (unsigned char)(pos | (Snew << 1) | (Sold << 2));
-            nS += (int)Snew;
-            if (Snew) as += ad;
-          }
-          delta = s_run - incoming;
-          used_in = incoming;
-        }
+        scan = viol;
+        if (viol) used_in = incoming;
       }
       rounds_total += rounds;
       // ---- draw_kappa_tau (:345-377)
@@ -300,6 +303,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       swaa = warp_sum(swaa);
       as = warp_sum(as);
       nS = warp_sum(nS);
+      const int nw = T >> 5;
       __syncthreads();
       if (lane == 0) {
         red[warp] = sw;
@@ -358,10 +362,8 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     // ---- fold of the last sweep, write-back
     if (prev_ret) {
       const float cA1 = pt, cA2 = pt * pk, cQ = -0.5f * pt * pt;
-      for (int j = 0; j < g; ++j) {
-        const int i = tid * g + j;
-        if (i >= N) break;
-        const int slot = j * T + tid;
+      for (int j = 0; j < gcount; ++j) {
+        const int slot = gslot(i0 + j, pad);
         const unsigned int Sold = (fl_s[slot] >> 1) & 1u;
         const float wold = w_s[slot];
         accA[slot] += ((float)Sold - 0.5f) * cA1 - wold * cA2;
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     }
     __syncthreads();
     for (int i = tid; i < N; i += T) {
-      int slot = (i % g) * T + i / g;
+      const int slot = gslot(i, pad);
       a.cnt[(size_t)l * N + i] = cnt_s[slot];
       if (a.w_out) a.w_out[(size_t)l * N + i] = w_s[slot];
       if (a.S_out) a.S_out[(size_t)l * N + i] = (fl_s[slot] >> 1) & 1u;
@@ -485,16 +487,21 @@ static void sc_pick_geometry(ScShard* s) {
   T = std::max(64, std::min(maxT / 32 * 32, T));
   s->T = T;
   s->g = (s->N + T - 1) / T;
-  s->slots = s->T * s->g;
   const size_t fixed = 160 * 8 + 4 * 8 + 4 * 4;
-  size_t small = fixed + (size_t)s->slots * 7, big = fixed + (size_t)s->slots * 15;
+  s->pad = 1;
+  s->slots = ((s->T * s->g + 31) / 32) * 33 + 32;  // gslot(): one pad word per 32 genes
+  if (fixed + (size_t)s->slots * 11 + 16 > (size_t)prop.sharedMemPerBlockOptin) {
+    s->pad = 0;  // very long gene vectors: give up the padding rather than the residency
+    s->slots = s->T * s->g;
+  }
+  size_t small = fixed + (size_t)s->slots * 11, big = fixed + (size_t)s->slots * 19;
   int acc_limit = 32 * 1024;
   if (const char* e = getenv("URSM_SC_ACC_SMEM_LIMIT")) acc_limit = atoi(e);
   s->acc_smem = big <= (size_t)acc_limit;
   s->smem = (int)((s->acc_smem ? big : small) + 16);
   URSM_REQUIRE((size_t)s->smem <= (size_t)prop.sharedMemPerBlockOptin,
                "gene count too large for the chain-resident single-cell kernel "
-               "(7 bytes of shared memory per gene)");
+               "(11 bytes of shared memory per gene)");
   if (s->acc_smem) {
     URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem));
@@ -544,7 +551,7 @@ static void sc_finish_create(ScShard* s, const int64_t* h_G) {
   s->counter.alloc(1);
   s->A.alloc((size_t)s->N * s->K);
   sc_pick_geometry(s);
-  s->Aslot.alloc((size_t)s->K * s->slots);
+  s->Aslot.alloc((size_t)s->K * s->N);
   s->sample = 1;
   URSM_CUDA(cudaDeviceSynchronize());
 }
@@ -554,13 +561,14 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
   a.G = s->G.p;
   a.R = s->R.p;
   a.order = s->order.p;
-  a.Aslot = s->Aslot.p;
+  a.A32 = s->Aslot.p;
   a.L = s->L;
   a.N = s->N;
   a.K = s->K;
   a.cell_offset = s->cell_offset;
   a.g = s->g;
   a.slots = s->slots;
+  a.pad = s->pad;
   a.mu_k = s->pkappa[0];
   a.prec_k = 1.0 / s->pkappa[1];
   a.mu_t = s->ptau[0];
@@ -674,10 +682,9 @@ int ursm_sc_set_params(ursm_sc* sc, const double* h_A, const double* h_pkappa,
   URSM_REQUIRE(h_pkappa[1] > 0 && h_ptau[1] > 0, "ursm_sc_set_params: prior variance must be > 0");
   const int N = s->N, K = s->K;
   URSM_CUDA(cudaMemcpy(s->A.p, h_A, (size_t)N * K * sizeof(double), cudaMemcpyHostToDevice));
-  std::vector<float> slot((size_t)K * s->slots, 0.f);
+  std::vector<float> slot((size_t)K * N, 0.f);  // A^T in fp32, gene order
   for (int k = 0; k < K; ++k)
-    for (int i = 0; i < N; ++i)
-      slot[(size_t)k * s->slots + (size_t)(i % s->g) * s->T + i / s->g] = (float)h_A[(size_t)i * K + k];
+    for (int i = 0; i < N; ++i) slot[(size_t)k * N + i] = (float)h_A[(size_t)i * K + k];
   URSM_CUDA(cudaMemcpy(s->Aslot.p, slot.data(), slot.size() * sizeof(float),
                        cudaMemcpyHostToDevice));
   s->pkappa[0] = h_pkappa[0];
