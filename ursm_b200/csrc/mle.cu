@@ -31,7 +31,7 @@ struct Mle {
   const double* coeffA = nullptr;
   DevBuf<double> u, ratio;               // [L] u_l and R_l / u_l
   DevBuf<int> act_cur, act_next;         // [K] columns in opt_Ak at the start / end of an iteration
-  DevBuf<int> niter, base, halv;         // [K] outer iterations, halvings already tried, total halvings
+  DevBuf<int> niter, base, halv, win;    // [K] outer iterations, halvings already tried, total halvings
   DevBuf<double> cand;                   // [K][kCand][N] candidate columns of one backtracking batch
   DevBuf<double> cres;                   // [K][kCand][4]: accepted?, objective, ||dA||_1, step
   DevBuf<double> delta;                  // [K] last accepted ||dA_k||_1
@@ -47,55 +47,95 @@ constexpr int kColThreads = 256;
 
 // MODE 0: out[type][i] += Y_li * E[S_li]            (m_step.py:88-89)
 // MODE 1: out[type][i] += E[S_li] * R_l / u_l       (m_step.py:123-125), active types only
-// A thread owns two adjacent genes and walks a chunk of the type-sorted cells; the
-// counters are read as one 32-bit word per cell (coalesced), `ratio` = R_l/u_l comes
-// from mle_u_kernel.
+// A thread owns four adjacent genes (one 64-bit load of counters per cell) and walks a
+// chunk of the type-sorted cells, four cells per trip so that four independent loads
+// are in flight; `ratio` = R_l/u_l comes from mle_u_kernel.  HBM-bound: 2 B per
+// cell x gene (MODE 0 adds the 4 B count).
+constexpr int kColGenes = 4;
+
 template <int MODE>
 __global__ void __launch_bounds__(kColThreads)
 mle_colsum_kernel(const float* Y, const unsigned short* cnt, const int* G, const int* order,
                   const double* ratio, const int* active, long long L, int N, int chunk,
                   double inv_sample, double* out) {
-  const int i = 2 * (blockIdx.x * kColThreads + threadIdx.x);
+  const int i = kColGenes * (blockIdx.x * kColThreads + threadIdx.x);
   const long long c0 = (long long)blockIdx.y * chunk, c1 = min(L, c0 + chunk);
   if (i >= N) return;
-  const bool pair = (i + 1 < N) && ((N & 1) == 0);  // 32-bit loads need even row strides
-  double acc0 = 0.0, acc1 = 0.0;
+  const bool vec = (i + 3 < N) && ((N & 3) == 0);  // 64-bit loads need 8-byte aligned rows
+  double acc[kColGenes] = {0.0, 0.0, 0.0, 0.0};
   int cur = -1;
-  for (long long c = c0; c < c1; ++c) {
-    const int l = order[c];
-    const int type = G[l];
-    if (type != cur) {
-      if (cur >= 0) {
-        if (acc0 != 0.0) atomicAdd(&out[(size_t)cur * N + i], acc0);
-        if (acc1 != 0.0) atomicAdd(&out[(size_t)cur * N + i + 1], acc1);
-      }
-      acc0 = acc1 = 0.0;
-      cur = type;
-    }
-    if (MODE == 1 && !active[type]) continue;
+  auto flush = [&]() {
+    if (cur < 0) return;
+#pragma unroll
+    for (int q = 0; q < kColGenes; ++q)
+      if (acc[q] != 0.0 && i + q < N) atomicAdd(&out[(size_t)cur * N + i + q], acc[q]);
+#pragma unroll
+    for (int q = 0; q < kColGenes; ++q) acc[q] = 0.0;
+  };
+  auto load4 = [&](int l, unsigned int& lo, unsigned int& hi) {
     const unsigned short* row = cnt + (size_t)l * N + i;
-    unsigned int c01;
-    if (pair) {
-      c01 = *reinterpret_cast<const unsigned int*>(row);
+    if (vec) {
+      const uint2 v = *reinterpret_cast<const uint2*>(row);
+      lo = v.x;
+      hi = v.y;
     } else {
-      c01 = row[0];
-      if (i + 1 < N) c01 |= (unsigned int)row[1] << 16;
+      lo = row[0];
+      hi = 0u;
+      if (i + 1 < N) lo |= (unsigned int)row[1] << 16;
+      if (i + 2 < N) hi = row[2];
+      if (i + 3 < N) hi |= (unsigned int)row[3] << 16;
     }
-    const double e0 = (double)(c01 & 0xffffu) * inv_sample, e1 = (double)(c01 >> 16) * inv_sample;
-    if (MODE == 0) {
-      const float* y = Y + (size_t)l * N + i;
-      acc0 += (double)y[0] * e0;
-      if (i + 1 < N) acc1 += (double)y[1] * e1;
-    } else {
-      const double r = ratio[l];
-      acc0 += e0 * r;
-      acc1 += e1 * r;
+  };
+  for (long long c = c0; c < c1; c += 4) {
+    int l[4], ty[4];
+    unsigned int lo[4], hi[4];
+    double w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool ok = c + q < c1;
+      l[q] = ok ? order[c + q] : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ty[q] = l[q] >= 0 ? G[l[q]] : -1;
+      const bool use = ty[q] >= 0 && (MODE == 0 || active[ty[q]]);
+      if (!use) ty[q] = ty[q] >= 0 ? -2 - ty[q] : -1;  // keep the type for flushing, skip the row
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      lo[q] = hi[q] = 0u;
+      w[q] = 0.0;
+      if (ty[q] >= 0) {
+        load4(l[q], lo[q], hi[q]);
+        w[q] = (MODE == 1) ? ratio[l[q]] * inv_sample : inv_sample;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (l[q] < 0) continue;
+      const int type = ty[q] >= 0 ? ty[q] : -2 - ty[q];
+      if (type != cur) {
+        flush();
+        cur = type;
+      }
+      if (ty[q] < 0) continue;
+      const double e0 = (double)(lo[q] & 0xffffu), e1 = (double)(lo[q] >> 16);
+      const double e2 = (double)(hi[q] & 0xffffu), e3 = (double)(hi[q] >> 16);
+      if (MODE == 0) {
+        const float* y = Y + (size_t)l[q] * N + i;
+        acc[0] += (double)y[0] * e0 * w[q];
+        if (i + 1 < N) acc[1] += (double)y[1] * e1 * w[q];
+        if (i + 2 < N) acc[2] += (double)y[2] * e2 * w[q];
+        if (i + 3 < N) acc[3] += (double)y[3] * e3 * w[q];
+      } else {
+        acc[0] += e0 * w[q];
+        acc[1] += e1 * w[q];
+        acc[2] += e2 * w[q];
+        acc[3] += e3 * w[q];
+      }
     }
   }
-  if (cur >= 0) {
-    if (acc0 != 0.0) atomicAdd(&out[(size_t)cur * N + i], acc0);
-    if (acc1 != 0.0 && i + 1 < N) atomicAdd(&out[(size_t)cur * N + i + 1], acc1);
-  }
+  flush();
 }
 
 // u_l = sum_i A[i, G_l] E[S_li] and ratio_l = R_l / u_l  (one warp per cell; active types)
@@ -112,12 +152,35 @@ __global__ void mle_u_kernel(const unsigned short* cnt, const int* G, const doub
   double s = 0.0;
   if ((N & 3) == 0) {  // 64-bit loads: four counters per lane and trip
     const uint2* row4 = reinterpret_cast<const uint2*>(row);
-    for (int q = lane; q < (N >> 2); q += 32) {
-      const uint2 c = row4[q];
-      const double* a4 = Ak + 4 * q;
-      s += a4[0] * (double)(c.x & 0xffffu) + a4[1] * (double)(c.x >> 16) +
-           a4[2] * (double)(c.y & 0xffffu) + a4[3] * (double)(c.y >> 16);
+    const int n4 = N >> 2;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int q = lane; q < n4; q += 128) {  // four independent 8-byte loads in flight
+      const uint2 z = make_uint2(0u, 0u);
+      const int q1 = q + 32, q2 = q + 64, q3 = q + 96;
+      const uint2 c0 = row4[q];
+      const uint2 c1 = q1 < n4 ? row4[q1] : z;
+      const uint2 c2 = q2 < n4 ? row4[q2] : z;
+      const uint2 c3 = q3 < n4 ? row4[q3] : z;
+      const double* a0 = Ak + 4 * q;
+      s += a0[0] * (double)(c0.x & 0xffffu) + a0[1] * (double)(c0.x >> 16) +
+           a0[2] * (double)(c0.y & 0xffffu) + a0[3] * (double)(c0.y >> 16);
+      if (q1 < n4) {
+        const double* a1 = Ak + 4 * q1;
+        s1 += a1[0] * (double)(c1.x & 0xffffu) + a1[1] * (double)(c1.x >> 16) +
+              a1[2] * (double)(c1.y & 0xffffu) + a1[3] * (double)(c1.y >> 16);
+      }
+      if (q2 < n4) {
+        const double* a2 = Ak + 4 * q2;
+        s2 += a2[0] * (double)(c2.x & 0xffffu) + a2[1] * (double)(c2.x >> 16) +
+              a2[2] * (double)(c2.y & 0xffffu) + a2[3] * (double)(c2.y >> 16);
+      }
+      if (q3 < n4) {
+        const double* a3 = Ak + 4 * q3;
+        s3 += a3[0] * (double)(c3.x & 0xffffu) + a3[1] * (double)(c3.x >> 16) +
+              a3[2] * (double)(c3.y & 0xffffu) + a3[3] * (double)(c3.y >> 16);
+      }
     }
+    s += s1 + s2 + s3;
   } else {
     for (int i = lane; i < N; i += 32) s += Ak[i] * (double)row[i];
   }
@@ -265,40 +328,47 @@ __global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
   }
 }
 
-// Per column: accept the first passing trial of the batch (or schedule the next batch of
-// halvings), advance the opt_Ak loop state (:164-181).
-__global__ void mle_commit_kernel(double* A, const double* cand, const double* cres,
-                                  const int* act, int* act_next, int* niter, int* base, int* halv,
-                                  double* delta, int N, double conv, int maxiter) {
-  const int k = blockIdx.x;
+// Per column (one thread each): accept the first passing trial of the batch (or
+// schedule the next batch of halvings) and advance the opt_Ak loop state (:164-181).
+// win[k] = index of the accepted trial, -1 if none.
+__global__ void mle_decide_kernel(const double* cres, const int* act, int* act_next, int* niter,
+                                  int* base, int* halv, double* delta, int* win, int K,
+                                  double conv, int maxiter) {
+  const int k = threadIdx.x;
+  if (k >= K) return;
+  win[k] = -1;
   if (!act[k]) {
-    if (threadIdx.x == 0) act_next[k] = 0;
+    act_next[k] = 0;
     return;
   }
-  int win = -1;
+  int w = -1;
   for (int c = 0; c < kCand; ++c)
     if (cres[((size_t)k * kCand + c) * 4] != 0.0) {
-      win = c;
+      w = c;
       break;
     }
-  if (win < 0 && base[k] + kCand >= 1024) win = kCand - 1;  // step underflow guard
-  if (win < 0) {  // every trial of this batch was rejected: keep halving
-    if (threadIdx.x == 0) {
-      base[k] += kCand;
-      act_next[k] = 1;
-    }
+  if (w < 0 && base[k] + kCand >= 1024) w = kCand - 1;  // step underflow guard
+  if (w < 0) {  // every trial of this batch was rejected: keep halving
+    base[k] += kCand;
+    act_next[k] = 1;
     return;
   }
-  const double* src = cand + ((size_t)k * kCand + win) * N;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) A[(size_t)k * N + i] = src[i];
-  if (threadIdx.x == 0) {
-    const double d = cres[((size_t)k * kCand + win) * 4 + 2];
-    delta[k] = d;
-    halv[k] += base[k] + win;
-    base[k] = 0;
-    const int n = ++niter[k];
-    act_next[k] = (d > conv && n < maxiter) ? 1 : 0;
-  }
+  const double d = cres[((size_t)k * kCand + w) * 4 + 2];
+  win[k] = w;
+  delta[k] = d;
+  halv[k] += base[k] + w;
+  base[k] = 0;
+  const int n = ++niter[k];
+  act_next[k] = (d > conv && n < maxiter) ? 1 : 0;
+}
+
+// A[k] <- accepted trial column
+__global__ void mle_copy_kernel(double* A, const double* cand, const int* win, int N) {
+  const int k = blockIdx.x, w = win[k];
+  if (w < 0) return;
+  const double* src = cand + ((size_t)k * kCand + w) * N;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < N; i += gridDim.y * blockDim.x)
+    A[(size_t)k * N + i] = src[i];
 }
 
 // part[k][:] <- part_local[k][:] for the columns that were stepped; the per-type
@@ -410,6 +480,7 @@ int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t
     m->niter.alloc(K);
     m->base.alloc(K);
     m->halv.alloc(K);
+    m->win.alloc(K);
     m->delta.alloc(K);
     m->act_cur.zero();
     m->act_next.zero();
@@ -465,7 +536,7 @@ int ursm_mle_begin(ursm_mle* mm, double* d_part, void* stream) {
   URSM_CUDA(cudaMemsetAsync(d_part, 0, (size_t)m->K * m->N * sizeof(double), st));
   if (m->sc) {
     ScShard* s = m->sc;
-    const int gx = (m->N + 2 * kColThreads - 1) / (2 * kColThreads);
+    const int gx = (m->N + kColGenes * kColThreads - 1) / (kColGenes * kColThreads);
     int ny;
     const int chunk = colsum_chunk(m, s->L, gx, &ny);
     mle_colsum_kernel<0><<<dim3(gx, ny), kColThreads, 0, st>>>(
@@ -486,7 +557,7 @@ static void mle_pass(Mle* m, double* d_part, cudaStream_t st) {
                                                            m->act_cur.p, s->L, m->N, inv, m->u.p,
                                                            m->ratio.p);
   URSM_LAUNCH_CHECK();
-  const int gx = (m->N + 2 * kColThreads - 1) / (2 * kColThreads);
+  const int gx = (m->N + kColGenes * kColThreads - 1) / (kColGenes * kColThreads);
   int ny;
   const int chunk = colsum_chunk(m, s->L, gx, &ny);
   mle_colsum_kernel<1><<<dim3(gx, ny), kColThreads, 0, st>>>(s->Y, s->cnt.p, s->G.p, s->order.p,
@@ -559,9 +630,11 @@ int ursm_mle_opt_step(ursm_mle* mm, const double* d_cconst_part, void* stream) {
   const int T = std::max(64, std::min(1024, (m->N / 4 + 31) / 32 * 32));
   mle_cand_kernel<<<dim3(kCand, m->K), T, 0, st>>>(a);
   URSM_LAUNCH_CHECK();
-  mle_commit_kernel<<<m->K, 256, 0, st>>>(m->A.p, m->cand.p, m->cres.p, m->act_cur.p,
-                                          m->act_next.p, m->niter.p, m->base.p, m->halv.p,
-                                          m->delta.p, m->N, m->conv, m->maxiter);
+  mle_decide_kernel<<<1, 32, 0, st>>>(m->cres.p, m->act_cur.p, m->act_next.p, m->niter.p,
+                                      m->base.p, m->halv.p, m->delta.p, m->win.p, m->K, m->conv,
+                                      m->maxiter);
+  URSM_LAUNCH_CHECK();
+  mle_copy_kernel<<<dim3(m->K, 8), 256, 0, st>>>(m->A.p, m->cand.p, m->win.p, m->N);
   URSM_LAUNCH_CHECK();
   URSM_API_END
 }
