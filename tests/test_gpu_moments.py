@@ -84,6 +84,32 @@ def test_bulk_split_moments_frozen_W(golden):
     np.testing.assert_allclose(bk.suff_stats["exp_Zik"].sum(axis=1), X.sum(axis=0), rtol=1e-12)
 
 
+def test_bulk_split_moments_large_counts():
+    """Deep samples (counts in the thousands): the BTRS branch of the binomial chain."""
+    import ursm_b200.e_step_gibbs as es
+    rs = np.random.RandomState(4)
+    M, N, K = 24, 96, 4
+    A = rs.dirichlet(np.ones(N) * 0.7, K).T
+    A = np.maximum(A, 1e-6)
+    A /= A.sum(axis=0)
+    W = rs.dirichlet(np.ones(K) * 1.5, M).T
+    X = rs.poisson(3.0e5 * A.dot(W).T).astype(float)      # mean count ~3000
+    bk = es.LogitNormalGibbs_BK(A, np.ones(K), X, seed=23)
+    bk.set_state(W)
+    bk.freeze = 1
+    S = 300
+    bk.gibbs(burnin=0, sample=S, thin=1, mean_approx=False)
+    AW = A.dot(W)
+    P = (A[None, :, :] * W.T[:, None, :]) / AW.T[:, :, None]
+    EZ, VZ = X[:, :, None] * P, X[:, :, None] * P * (1 - P)
+    for got, ax in ((bk.suff_stats["exp_Zik"], 0), (bk.suff_stats["exp_Zjk"], 1)):
+        z = _zscores(got, EZ.sum(axis=ax), np.sqrt(VZ.sum(axis=ax) / S))
+        assert np.abs(z).max() < 5.0
+        assert abs(np.mean(z * z) - 1.0) < 6.0 * np.sqrt(2.0 / z.size)
+        assert abs(np.mean(z)) < 5.0 / np.sqrt(z.size)
+    np.testing.assert_allclose(bk.suff_stats["exp_Zjk"].sum(axis=1), X.sum(axis=1), rtol=1e-12)
+
+
 def test_bulk_dirichlet_moments_frozen_Z():
     import ursm_b200.e_step_gibbs as es
     rs = np.random.RandomState(1)

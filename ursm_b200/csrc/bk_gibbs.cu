@@ -124,159 +124,104 @@ __global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
 
 // ---------------------------------------------------------------------------
 // draw_Z (:132-138) for one Gibbs sweep: Z_ji. ~ Mult(X_ji, W_.j A_i. / AW_ij) as a
-// chain of K-1 conditional binomials.  The binomials are data-dependent loops
-// (inversion takes ~n p steps, BTRS is a rejection sampler whose exact test is ~10x the
-// cost of its squeeze), so the work is scheduled dynamically INSIDE each warp:
-//   * a warp owns 32 genes x the CTA's chunk of bulk samples = a queue of entries;
-//     a lane that finishes an entry takes the next one (ballot + popc, no atomics);
-//   * every trip of the warp loop gives each lane a bounded slice of work on its own
-//     current (entry, type) item -- 8 inversion steps or one BTRS attempt
-//     (samplers.cuh::BinomState).
-// X is stored with its columns sorted by total count, so the 32 genes of a warp have
-// similar depth.  Z is consumed on the spot: sum_i Z_jik and sum_j Z_jik go to
-// shared-memory integer counters (flushed once per CTA).  Arithmetic is fp32 on
-// ratios of positive suffix sums (no cancellation); counts are exact integers; the
-// RNG is keyed on the ORIGINAL gene id and the global sample id, so results depend
-// neither on the sort nor on the sharding.
+// chain of K-1 conditional binomials (what numpy.random.multinomial does).
+// A thread owns one gene (its A row in registers) and walks the CTA's chunk of bulk
+// samples; the 32 lanes of a warp work on the same (sample, type) item in lock step, so
+// set-up, RNG and the consumption of Z are full-width and sum_i Z_jik is a warp
+// reduction + one shared-memory atomic per warp.  The data-dependent part -- fp32
+// inversion (n r <= 40) or BTRS (samplers.cuh::BinomState) -- diverges only by the
+// spread of n r inside the warp, which is small because X is stored with its columns
+// SORTED by total count: the 32 genes of a warp have similar depth and sit in the same
+// regime.  Z is never stored: sum_j Z_jik accumulates in registers and is flushed once
+// per CTA.  Probabilities are ratios of positive masses (the mass of the types still to
+// come is tracked in fp64); counts are exact integers; the RNG is keyed on the ORIGINAL
+// gene id and the global sample id, so results depend neither on the sort nor on the
+// sharding.
 // ---------------------------------------------------------------------------
 constexpr int kSplitThreads = 256;
 
-__global__ void __launch_bounds__(kSplitThreads) bk_split_kernel(BkTileArgs a) {
+__global__ void __launch_bounds__(kSplitThreads, 3) bk_split_kernel(BkTileArgs a) {
   extern __shared__ __align__(16) unsigned char split_smem[];
-  const int tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int K = a.K, N = a.N;
   const long long j0 = (long long)blockIdx.y * a.chunk;
   const long long j1 = min(a.M, j0 + a.chunk);
   const int nloc = (int)(j1 - j0);
   float* Wsm = reinterpret_cast<float*>(split_smem);                      // [chunk][K]
   unsigned int* Jsm = reinterpret_cast<unsigned int*>(Wsm + a.chunk * K);  // [chunk][K]
-  float* As = reinterpret_cast<float*>(Jsm + a.chunk * K);                 // [K][T] by gene slot
-  float* suf = As + K * kSplitThreads;                                     // [K+1][T] by thread
-  unsigned int* accI = reinterpret_cast<unsigned int*>(suf + (K + 1) * kSplitThreads);  // [K][T]
-  int* gene_of = reinterpret_cast<int*>(accI + K * kSplitThreads);         // [T] original gene id
+  float* Ar = reinterpret_cast<float*>(Jsm + a.chunk * K) + tid;            // [K][T], own column
+  unsigned int* accI = reinterpret_cast<unsigned int*>(Ar - tid + K * kSplitThreads) + tid;
   for (int t = tid; t < nloc * K; t += kSplitThreads) {
     Wsm[t] = (float)a.W[j0 * K + t];
     Jsm[t] = 0u;
   }
-  {
-    const int gi = blockIdx.x * kSplitThreads + tid;
-    const bool in = gi < N;
-    const int gene = in ? a.perm[gi] : -1;
-    gene_of[tid] = gene;
-    for (int k = 0; k < K; ++k) {
-      As[k * kSplitThreads + tid] = in ? (float)a.A[(size_t)k * N + gene] : 0.f;
-      accI[k * kSplitThreads + tid] = 0u;
-    }
-    suf[K * kSplitThreads + tid] = 0.f;
+  const int gi = blockIdx.x * kSplitThreads + tid;  // position in the sorted column order
+  const bool in = gi < N;
+  const int gene = in ? a.perm[gi] : 0;             // original gene id
+  for (int k = 0; k < K; ++k) {
+    Ar[k * kSplitThreads] = in ? (float)a.A[(size_t)k * N + gene] : 0.f;
+    accI[k * kSplitThreads] = 0u;
   }
   __syncthreads();
-
-  const int gwarp = blockIdx.x * kSplitThreads + wbase;  // first sorted gene of this warp
-  const int total = (gwarp < N) ? 32 * nloc : 0;          // entries in the warp's queue
-  int cursor = 0;                                         // warp-uniform
-  bool need = true, active = false;
-  int jl = 0, slot = 0, gene = 0, k = 0, rem = 0, nw = 0;
-  bool item = false;
-  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-  BinomState b;
-  b.mode = kBinDone;
   const uint32_t ctr2 = kPurposeBulkZ | a.sweep;
 
-  auto next_uniform = [&]() -> float {
-    if ((nw & 3) == 0)
-      philox_block(a.key, (uint32_t)gene, (uint32_t)(a.sample_offset + j0 + jl), ctr2,
-                   (uint32_t)(nw >> 2), w0, w1, w2, w3);
-    const int sel = nw & 3;
-    ++nw;
-    const uint32_t w = sel == 0 ? w0 : (sel == 1 ? w1 : (sel == 2 ? w2 : w3));
-    return u01(w);
-  };
-
-  while (true) {
-    // ---- hand the next entries of the queue to the lanes that are free
-    const unsigned int free_mask = __ballot_sync(0xffffffffu, need);
-    if (need) {
-      const int e = cursor + __popc(free_mask & ((1u << lane) - 1u));
-      need = false;
-      if (e < total) {
-        jl = e >> 5;
-        slot = wbase + (e & 31);
-        gene = gene_of[slot];
-        const float xf = (gene >= 0) ? a.X[(size_t)(j0 + jl) * N + gwarp + (e & 31)] : 0.f;
-        if (xf == 0.f) {
-          need = true;  // nothing to split: take another entry next trip
-        } else {
-          rem = (int)xf;
-          const float* Wj = Wsm + jl * K;
-          float acc = 0.f;
-          for (int kk = K - 1; kk >= 0; --kk) {  // suffix sums of W_kj A_ik (all positive)
-            acc += Wj[kk] * As[kk * kSplitThreads + slot];
-            suf[kk * kSplitThreads + tid] = acc;
-          }
-          k = 0;
-          nw = 0;
-          item = false;
-          active = true;
-        }
-      }
-    }
-    cursor += __popc(free_mask);
-    if (!__any_sync(0xffffffffu, active || need)) break;
-    // ---- (A) open the next (entry, type) item
-    if (active && !item) {
-      if (k == K - 1 || rem == 0) {
-        // the last type takes what is left (also closes an exhausted entry)
-        if (rem > 0) {
-          atomicAdd(&Jsm[jl * K + k], (unsigned int)rem);
-          atomicAdd(&accI[k * kSplitThreads + slot], (unsigned int)rem);
-        }
-        active = false;
-        need = true;
+  for (int jl = 0; jl < nloc; ++jl) {
+    const float* Wj = Wsm + jl * K;
+    const float xf = in ? a.X[(size_t)(j0 + jl) * N + gi] : 0.f;
+    int rem = (int)xf;
+    if (__all_sync(0xffffffffu, rem == 0)) continue;  // nothing to split in this warp
+    const uint32_t jg = (uint32_t)(a.sample_offset + j0 + jl);
+    // AW_ij and the mass of the types still to come (fp64: exact enough down to the last type)
+    double rest = 0.0;
+    for (int k = 0; k < K; ++k) rest += (double)(Wj[k] * Ar[k * kSplitThreads]);
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      int z;
+      if (k == K - 1) {
+        z = rem;  // the last type takes what is left
       } else {
-        const float sk = suf[k * kSplitThreads + tid];
-        const float sn = suf[(k + 1) * kSplitThreads + tid];
-        const float inv = URSM_DIV(1.0f, sk);
-        const float pc = sn * inv;  // P(not type k | not yet assigned)
-        // W_kj A_ik / suffix, formed from the product itself when it is the small side
-        const float qk = Wsm[jl * K + k] * As[k * kSplitThreads + slot];
-        const float pk = (sk - sn) * inv;
-        binom_begin(b, rem, (pk < 0.5f) ? qk * inv : pk, pc, next_uniform());
-        item = true;
-      }
-    }
-    // ---- (B) inversion: up to 8 CDF steps, ended early by a warp vote
-    for (int it = 0; it < 8; ++it) {
-      const bool stepping = active && item && b.mode == kBinInv;
-      if (!__any_sync(0xffffffffu, stepping)) break;
-      if (stepping) binom_inv_step(b);
-    }
-    // ---- (C) one BTRS attempt / restart of a failed inversion / commit
-    if (active && item) {
-      if (b.mode == kBinBtrs) {
-        const float U = next_uniform(), V = next_uniform();
-        binom_btrs_attempt(b, U, V);
-      } else if (b.mode == kBinRetry) {
-        binom_inv_start(b, next_uniform());
-      }
-      if (b.mode == kBinDone) {
-        const int z = b.result;
-        if (z > 0) {
-          atomicAdd(&Jsm[jl * K + k], (unsigned int)z);
-          atomicAdd(&accI[k * kSplitThreads + slot], (unsigned int)z);
-          rem -= z;
+        if ((k & 3) == 0) philox_block(a.key, (uint32_t)gene, jg, ctr2, (uint32_t)(k >> 2), w0, w1, w2, w3);
+        const uint32_t wk = (k & 3) == 0 ? w0 : ((k & 3) == 1 ? w1 : ((k & 3) == 2 ? w2 : w3));
+        const float qk = Wj[k] * Ar[k * kSplitThreads];
+        const double after = fmax(rest - (double)qk, 0.0);
+        const float inv = URSM_DIV(1.0f, (float)rest);
+        BinomState b;
+        // P(type k | not yet assigned) and its complement, each formed from its own mass
+        binom_begin(b, rem, qk * inv, (float)after * inv, u01(wk));
+        rest = after;
+        int extra = 0;  // further Philox blocks of this item: BTRS attempts, inversion restarts
+        while (b.mode != kBinDone) {
+          if (b.mode == kBinInv) {
+            binom_inv_step(b);
+          } else {
+            uint32_t e0, e1, e2, e3;
+            philox_block(a.key, (uint32_t)gene, jg, ctr2, 0x100u + (uint32_t)(k << 8) + (uint32_t)extra,
+                         e0, e1, e2, e3);
+            ++extra;
+            if (b.mode == kBinBtrs) {
+              binom_btrs_attempt(b, u01(e0), u01(e1));
+              if (b.mode != kBinDone) binom_btrs_attempt(b, u01(e2), u01(e3));
+            } else {  // kBinRetry
+              binom_inv_start(b, u01(e0));
+            }
+          }
         }
-        ++k;
-        item = false;
+        z = b.result;
+        rem -= z;
       }
+      accI[k * kSplitThreads] += (unsigned int)z;
+      const unsigned int tot = __reduce_add_sync(0xffffffffu, (unsigned int)z);
+      if (lane == 0 && tot != 0u) atomicAdd(&Jsm[jl * K + k], tot);
     }
   }
   __syncthreads();
   for (int t = tid; t < nloc * K; t += kSplitThreads)
     if (Jsm[t] != 0u) atomicAdd(&a.sumJ[j0 * K + t], (double)Jsm[t]);
-  if (gene_of[tid] >= 0 && a.accumulate_I) {
-    for (int kk = 0; kk < K; ++kk) {
-      const unsigned int v = accI[kk * kSplitThreads + tid];
-      if (v != 0u) atomicAdd(&a.sumI[(size_t)kk * N + gene_of[tid]], (double)v * a.scaleI);
+  if (in && a.accumulate_I) {
+    for (int k = 0; k < K; ++k) {
+      const unsigned int v = accI[k * kSplitThreads];
+      if (v != 0u) atomicAdd(&a.sumI[(size_t)k * N + gene], (double)v * a.scaleI);
     }
   }
 }
@@ -292,16 +237,15 @@ static void bk_launch_split(BkShard* b, BkTileArgs& a, cudaStream_t st) {
   a.sample_offset = b->sample_offset;
   const int K = b->K;
   const int gx = (b->N + kSplitThreads - 1) / kSplitThreads;
-  const size_t per_thread = (size_t)(3 * K + 2) * kSplitThreads * 4;
-  // a chunk's W rows and per-sample sums (8 B per sample and type) share the CTA's smem
+  // a chunk's W rows and per-sample sums (8 B per sample and type): at most 24 KB of smem
   const long long max_chunk = std::max<long long>(1, (long long)(24 * 1024) / (8 * (long long)K));
-  long long want_y = std::max<long long>(1, (long long)(4 * b->num_sms + gx - 1) / gx);
+  long long want_y = std::max<long long>(1, (long long)(6 * b->num_sms + gx - 1) / gx);
   want_y = std::max<long long>(want_y, (b->M + max_chunk - 1) / max_chunk);
   long long ny = std::min<long long>(b->M, want_y);
   a.chunk = (int)((b->M + ny - 1) / ny);
   ny = (b->M + a.chunk - 1) / a.chunk;
   URSM_REQUIRE(ny <= 65535, "bulk split kernel: too many sample chunks");
-  const size_t smem = per_thread + (size_t)a.chunk * K * 8;
+  const size_t smem = (size_t)a.chunk * K * 8 + (size_t)2 * K * kSplitThreads * 4;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     URSM_CUDA(cudaFuncSetAttribute(bk_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

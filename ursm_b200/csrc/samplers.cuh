@@ -337,8 +337,8 @@ URSM_HD int binomial(int n, double p, RNG& rng) {
 // Binomial(n, p) as a resumable state machine in fp32 for the bulk split kernel
 // (csrc/bk_gibbs.cu::bk_split_kernel): lanes of a warp interleave "a few inversion
 // steps" / "one BTRS attempt" instead of each running its own data-dependent loop.
-//   n r <= 40  sequential inversion from 0 (as binomial_inversion above), fp32;
-//   n r  > 40  BTRS, Hormann's transformed rejection with squeeze (1993): the
+//   n r <= 20  sequential inversion from 0 (as binomial_inversion above), fp32;
+//   n r  > 20  BTRS, Hormann's transformed rejection with squeeze (1993): the
 //              86% quick-accept path in fp32, the exact log-ratio test in fp64.
 // `p` and its complement are passed separately (both are ratios of positive sums in
 // the caller), so 1 - p is never formed by subtraction.
@@ -351,13 +351,17 @@ struct BinomState {
   bool flip;
 };
 
-// n r above which BTRS replaces inversion (BTRS needs n r >= 10; pmf(0) >= e^-56 stays a
+// n r above which BTRS replaces inversion (BTRS needs n r >= 10; pmf(0) >= e^-28 stays a
 // normal fp32 number up to here)
-#define URSM_BINOM_INV_MAX 40.0f
+#define URSM_BINOM_INV_MAX 20.0f
 
 URSM_HD void binom_inv_start(BinomState& b, float u) {
   // pmf(0) = (1-r)^n
-  b.px = URSM_EXPF((float)b.n * log1pf(-b.r));
+  // log(1 - r): series below r = 1/16 (relative error < 1e-8), log of the complement above
+  const float r = b.r;
+  const float ser = -r * fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, 1.0f / 6, 0.2f), 0.25f), 1.0f / 3),
+                                      0.5f), 1.0f);
+  b.px = URSM_EXPF((float)b.n * ((r < 0.0625f) ? ser : URSM_LOGF(b.rc)));
   b.x = 0;
   b.u = u;
   b.mode = kBinInv;
@@ -378,7 +382,8 @@ URSM_HD void binom_begin(BinomState& b, int n, float p, float pc, float u) {
   if (nr <= URSM_BINOM_INV_MAX) {
     b.s = URSM_DIV(b.r, b.rc);
     b.c = (float)(n + 1) * b.s;
-    const int guard = (int)(nr + 10.0f * sqrtf(nr * b.rc + 1.0f));
+    const float var1 = fmaf(nr, b.rc, 1.0f);
+    const int guard = (int)(nr + 10.0f * var1 * URSM_RSQRT(var1));
     b.bound = guard < n ? guard : n;
     binom_inv_start(b, u);
   } else {
