@@ -52,6 +52,18 @@ METRIC = "gibbs_cell_gene_updates_per_s"
 UNIT = "updates/s"
 
 
+def load_traffic(workload):
+    """Measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture,
+    committed under profiles/); None when no capture exists for the workload."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as fh:
+            ent = json.load(fh).get(workload)
+        return None if ent is None else int(ent["bytes"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -351,9 +363,11 @@ def gpu_main(args, cfg):
         k_ms = float(np.mean(sc_ms))
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "sc_gibbs_kernel", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": peak_src, "kernel_ms": k_ms,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": load_traffic(args.workload),
+                    "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel_ms": k_ms,
                     "bytes_per_update": b_per_update,
+                    "note": "chain-resident kernel: issue-bound, not HBM-bound (DESIGN.md 4.1)",
                     "updates_per_s_kernel": Ll * N * sweeps / (k_ms * 1e-3)}
     elif bk_ms:
         alg_bytes = 4.0 * Ml * N * sweeps
