@@ -15,7 +15,9 @@ Differences that a caller can observe (all deliberate):
     device-resident uint16 counters when somebody reads it;
   * random numbers come from counter-based Philox keyed on (seed, EM iteration,
     global cell/sample index, gene, sweep) instead of the unseeded global numpy
-    state, so runs are reproducible and independent of the GPU count.
+    state, so the chains of an E-step depend only on (seed, parameters, data) and not on
+    the GPU count (the K x N statistics are summed with floating-point atomics, so a whole
+    fit repeats to rounding, not bit for bit).
 """
 import ctypes
 import logging
