@@ -58,7 +58,6 @@ struct ScGibbsArgs {
   double* cellmom;      // [4][L]
   double* stats;        // coeffA[K][N] | coeffAsq[K][N] | elbo | sk | skk | st | stt
   float* scratch;       // [grid][2][slots]
-  int* counter;
   int flush_every;
   // debug (all optional)
   const unsigned char* S0;  // [L][N]
@@ -126,11 +125,11 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     accQ[s] = 0.f;
   }
 
-  while (true) {
+  // cells are dealt round-robin over the CTAs in type-sorted order: every cell costs the
+  // same, and a static assignment keeps the grouping of the fp32 partial sums (hence the
+  // statistics, to fp64 summation order) identical from run to run
+  for (long long c = blockIdx.x;; c += gridDim.x) {
     __syncthreads();
-    if (tid == 0) ibc[0] = atomicAdd(a.counter, 1);
-    __syncthreads();
-    const long long c = ibc[0];
     const bool finished = c >= a.L;
     const int l = finished ? 0 : a.order[c];
     const int type = finished ? -1 : a.G[l];
@@ -576,9 +575,7 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
   a.cnt = s->cnt.p;
   a.cellmom = s->cellmom.p;
   a.scratch = s->scratch.p;
-  a.counter = s->counter.p;
   a.flush_every = 16;
-  URSM_CUDA(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
   if (!s->ev0) {
     URSM_CUDA(cudaEventCreate(&s->ev0));
     URSM_CUDA(cudaEventCreate(&s->ev1));
