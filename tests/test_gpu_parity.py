@@ -269,3 +269,74 @@ def test_injected_state_roundtrip_large_ragged(ub):
     for k in ("exp_kappa", "exp_tau", "exp_kappasq", "exp_tausq", "coeffA", "coeffAsq",
               "exp_elbo_const"):
         np.testing.assert_allclose(sc.suff_stats[k], oc.suff_stats[k], rtol=1e-10, atol=1e-8)
+
+
+# ---------------------------------------------------------------------------
+# edge cases: a type without cells (closed-form column, m_step.py:149-153), K = 1,
+# a single cell / a single bulk sample
+# ---------------------------------------------------------------------------
+def test_mstep_with_empty_type_matches_oracle(ub):
+    rs = np.random.RandomState(9)
+    N, K, L, M = 83, 4, 17, 6
+    sim = orc.simulate(N=N, K=K, L=L, M=M, seed=5, G=rs.randint(0, 3, L), anchor=1, anti=1)
+    Y, X, G = sim["Y"], sim["X"], sim["G"]          # type 3 has no cells
+    itype = _itype(G, K)
+    A = orc.init_A(Y, X, K, itype, 1e-6)
+    pk, pt, al = np.array([-1., 0.01]), np.array([N, 0.01 * N], dtype=float), np.ones(K)
+    sc = ub.es.LogitNormalGibbs_SC(A, pk, pt, Y, G, itype)
+    bk = ub.es.LogitNormalGibbs_BK(A, al, X)
+    bk.init_gibbs()
+    osc = orc.OracleGibbsSC(A, pk, pt, Y, G, itype, rng=np.random.RandomState(0))
+    obk = orc.OracleGibbsBK(A, al, X)
+    obk.init_gibbs()
+    osc._zero_stats()
+    T = 3
+    for t in range(T):
+        S = ((Y > 0) | (rs.rand(L, N) < 0.4)).astype(np.int64)
+        w = rs.gamma(2.0, 0.1, (L, N))
+        kappa, tau = rs.normal(-1, 0.3, (1, L)), rs.normal(N, 2, (1, L))
+        sc.inject(w, S, kappa, tau, T, reset=(t == 0))
+        osc.S, osc.w, osc.kappa, osc.tau = S, w, kappa, tau
+        osc.accumulate(T)
+    bk.gibbs(mean_approx=True)
+    obk.gibbs(mean_approx=True)
+    st, ost = dict(sc.suff_stats), dict(osc.suff_stats)
+    st.update(bk.suff_stats)
+    ost.update(obk.suff_stats)
+    mle = ub.ms.LogitNormalMLE(X, Y, G, K, itype, True, True, A, al, pk, pt, 1e-6, 1, 1e-6, 80)
+    omle = orc.OracleMLE(X, Y, G, K, itype, True, True, A, al, pk, pt, 1e-6, 1, 1e-6, 80)
+    mle.update_suff_stats(st)
+    omle.update_suff_stats(ost)
+    np.testing.assert_allclose(mle.compute_elbo(), omle.compute_elbo(), rtol=1e-9)
+    mle.opt_kappa_tau()
+    omle.opt_kappa_tau()
+    mle.opt_alpha()
+    omle.opt_alpha()
+    mle.opt_A_u()
+    omle.opt_A_u()
+    np.testing.assert_allclose(mle.A[:, 3], omle.A[:, 3], rtol=1e-9, atol=1e-12)   # closed form
+    np.testing.assert_allclose(mle.A, omle.A, rtol=REL, atol=1e-9)
+    np.testing.assert_allclose(mle.alpha, omle.alpha, rtol=1e-8)
+    np.testing.assert_allclose(mle.compute_elbo(), omle.compute_elbo(), rtol=1e-7)
+
+
+def test_degenerate_sizes(ub):
+    """K = 1 bulk-only fit (deterministic) and a one-cell / one-sample joint E-step."""
+    sim = orc.simulate(N=40, K=1, L=0, M=5, seed=2, anchor=1, anti=1)
+    X = sim["X"]
+    gem = ub.gm.LogitNormalGEM(BKexpr=X, K=1, MLE_CONV=1e-6, MLE_maxiter=50, EM_CONV=1e-6,
+                               EM_maxiter=3)
+    ogem = orc.OracleGEM(BKexpr=X, K=1, MLE_CONV=1e-6, MLE_maxiter=50, EM_CONV=1e-6, EM_maxiter=3)
+    np.testing.assert_allclose(gem.gem()[3], ogem.gem()[3], rtol=1e-9)
+    np.testing.assert_allclose(gem.A, ogem.A, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(gem.suff_stats["exp_W"], 1.0, rtol=1e-12)
+    sim = orc.simulate(N=33, K=2, L=1, M=1, seed=4, G=np.array([1]), anchor=1, anti=1)
+    Y, X, G = sim["Y"], sim["X"], sim["G"]
+    gem = ub.gm.LogitNormalGEM(BKexpr=X, SCexpr=Y, K=2, G=G, burnin=3, sample=4, EM_maxiter=2,
+                               MLE_maxiter=20, bk_mean_approx=False, seed=1)
+    niter, elbo, _, path = gem.gem()
+    assert niter == 2 and np.isfinite(path).all() and np.isfinite(gem.A).all()
+    np.testing.assert_allclose(gem.A.sum(axis=0), 1.0, rtol=1e-9)
+    eS = np.asarray(gem.suff_stats["exp_S"])
+    assert eS.shape == (1, 33) and np.all(eS[Y > 0] == 1)
+    np.testing.assert_allclose(gem.suff_stats["exp_Zjk"].sum(), X.sum(), rtol=1e-12)
