@@ -169,6 +169,17 @@ int ursm_mle_get_u(ursm_mle* m, double* h_u);
  * (utils.py:8-31) -- parity hook for the M-step's inner kernel */
 int ursm_simplex_proj(const double* h_y, int32_t n, double min_y, double* h_out);
 
+/* ---- file contract of scUnif.py (:85-94), SURVEY 8f row 1 ---------------------------
+ * Headerless comma-separated matrices, byte-compatible with np.savetxt(delimiter=",")
+ * ('%.18e' per value) and np.loadtxt(delimiter=","); multi-threaded host code.
+ * ursm_csv_write_f64   mtx2csv :85-87
+ * ursm_csv_shape + ursm_csv_read_f64   load_from_file :90-94 (float matrices)
+ */
+int ursm_csv_write_f64(const char* path, const double* data, int64_t rows, int64_t cols,
+                       int32_t nthreads);
+int ursm_csv_shape(const char* path, int64_t* rows, int64_t* cols);
+int ursm_csv_read_f64(const char* path, double* out, int64_t rows, int64_t cols, int32_t nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libursm_b200.so")
-SOURCES = ["common.cu", "sc_gibbs.cu", "bk_gibbs.cu", "mle.cu"]
+SOURCES = ["common.cu", "sc_gibbs.cu", "bk_gibbs.cu", "mle.cu", "csv_io.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-rdc=false"]
 
@@ -39,7 +39,7 @@ def build_library(force=False, verbose=False):
     nvcc = _nvcc()
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        o = os.path.join(LIBDIR, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
             cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
@@ -53,7 +53,7 @@ def build_library(force=False, verbose=False):
             print(out)
     if force or procs or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs \
-            + ["-cudart", "static"]
+            + ["-cudart", "static", "-lpthread"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -18,14 +18,15 @@ import time
 
 import numpy as np
 
-from . import dist
+from . import csvio, dist
 from .gem import LogitNormalGEM
 
 
 def mtx2csv(filename, nparray):
-    """scUnif.py:85-87."""
-    with open(filename, "w") as handle:
-        np.savetxt(handle, nparray, delimiter=",")
+    """scUnif.py:85-87: np.savetxt(handle, nparray, delimiter=',') -- same bytes, written
+    by the multi-threaded native formatter (the L x N exp_S matrix is the bulk of a run's
+    output)."""
+    csvio.savetxt_csv(filename, nparray)
 
 
 def gem2csv(dirname, gem, prefix=""):
@@ -51,6 +52,8 @@ def load_from_file(filename, dtype=float, delimiter=","):
     """scUnif.py:90-94."""
     if filename is None:
         return None
+    if dtype is float and delimiter == ",":
+        return csvio.loadtxt_csv(filename)   # same values as np.loadtxt, parsed in parallel
     return np.loadtxt(filename, dtype=dtype, delimiter=delimiter)
 
 
