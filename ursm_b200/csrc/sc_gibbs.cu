@@ -59,6 +59,8 @@ struct ScGibbsArgs {
   double* stats;        // coeffA[K][N] | coeffAsq[K][N] | elbo | sk | skk | st | stt
   float* scratch;       // [grid][2][slots]
   int flush_every;
+  int* counter;
+  int acc_red;          // accumulate the scratch row with reductions (no L1 left)
   // debug (all optional)
   const unsigned char* S0;  // [L][N]
   const double* kt0;        // [2][L]
@@ -125,11 +127,11 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     accQ[s] = 0.f;
   }
 
-  // cells are dealt round-robin over the CTAs in type-sorted order: every cell costs the
-  // same, and a static assignment keeps the grouping of the fp32 partial sums (hence the
-  // statistics, to fp64 summation order) identical from run to run
-  for (long long c = blockIdx.x;; c += gridDim.x) {
+  while (true) {
     __syncthreads();
+    if (tid == 0) ibc[0] = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const long long c = ibc[0];
     const bool finished = c >= a.L;
     const int l = finished ? 0 : a.order[c];
     const int type = finished ? -1 : a.G[l];
@@ -215,8 +217,17 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
               if (prev_ret) {  // update_suffStats (:245-270) of the previous sweep
                 const unsigned int Sp = (fl_s[slot] >> 1) & 1u;
                 const float wold = w_s[slot];
-                accA[slot] += ((float)Sp - 0.5f) * cA1 - wold * cA2;
-                accQ[slot] += cQ * wold;
+                const float dA = ((float)Sp - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
+                if (ACC_SMEM || !a.acc_red) {
+                  accA[slot] += dA;
+                  accQ[slot] += dQ;
+                } else {
+                  // L2-resident scratch row and no L1 to speak of (long gene vectors):
+                  // fire-and-forget reductions (one lane per slot at a time, so they are
+                  // uncontended) instead of load-add-store round trips
+                  atomicAdd(&accA[slot], dA);
+                  atomicAdd(&accQ[slot], dQ);
+                }
                 cnt_s[slot] += (unsigned short)Sp;
               }
               psi = fmaf(ft, av, fk);
@@ -365,8 +376,14 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
         const int slot = gslot(i0 + j, pad);
         const unsigned int Sold = (fl_s[slot] >> 1) & 1u;
         const float wold = w_s[slot];
-        accA[slot] += ((float)Sold - 0.5f) * cA1 - wold * cA2;
-        accQ[slot] += cQ * wold;
+        const float dA = ((float)Sold - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
+        if (ACC_SMEM || !a.acc_red) {
+          accA[slot] += dA;
+          accQ[slot] += dQ;
+        } else {
+          atomicAdd(&accA[slot], dA);
+          atomicAdd(&accQ[slot], dQ);
+        }
         cnt_s[slot] += (unsigned short)Sold;
       }
     }
@@ -576,6 +593,9 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
   a.cellmom = s->cellmom.p;
   a.scratch = s->scratch.p;
   a.flush_every = 16;
+  a.counter = s->counter.p;
+  URSM_CUDA(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
+  a.acc_red = (!s->acc_smem && s->smem > 128 * 1024) ? 1 : 0;
   if (!s->ev0) {
     URSM_CUDA(cudaEventCreate(&s->ev0));
     URSM_CUDA(cudaEventCreate(&s->ev1));
