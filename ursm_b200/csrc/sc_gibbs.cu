@@ -1,35 +1,35 @@
 // Single-cell Gibbs E-step for sm_100a: e_step_gibbs.py:171-377 as ONE persistent
 // kernel.
 //
-// Design (DESIGN.md sec. 3):
+// Design (DESIGN.md sec. 4.1):
 //  * cells are independent inside an E-step (parameters frozen), so one CTA runs
 //    ALL burnin + sample*thin sweeps of a cell with the chain state on chip:
-//    per gene 4 B (w, fp32) + 2 B (E[S] counter) + 1 B (flags) of shared memory.
-//    HBM is touched once per cell: read the count row (which genes are zero),
-//    write the E[S] counters.  psi, w, S never exist in HBM (the reference keeps
-//    five L x N fp64/int64 arrays, :216-220,232).
-//  * thread t owns the contiguous gene run [t*g, (t+1)*g); run element j lives in
-//    shared-memory slot j*T + t (bank-conflict free, no padding).
-//  * draw_S (:326-342) is a sequential scan over the zero genes of a cell through
-//    the running sum_AS.  It is kept EXACT: each update is rewritten as
-//    "s_other > T_i" (samplers.cuh::s_threshold), a thread scans its own run
-//    assuming the sweep-start sum as its incoming value and records the smallest
-//    |s_other - T_i| it saw (its margin); a block-wide exclusive scan of the
-//    per-thread net changes gives every thread its true incoming sum; only
-//    threads whose incoming sum moved by more than their margin re-scan (their
-//    uniforms are regenerated from the same Philox counter); repeat to the fixed
-//    point, which is the unique sequential solution.
-//  * draw_w (:318-323) is a rejection sampler; lanes of a warp run ATTEMPTS in lock
-//    step (one Philox block and a fixed amount of arithmetic each,
-//    samplers.cuh::pg_attempt) while every lane advances through its own genes, so
-//    divergence costs only the spread of the per-thread attempt totals.
+//    per gene 4 B (w, fp32) + 4 B (draw_S threshold) + 2 B (E[S] counter) + 1 B (flags)
+//    of shared memory.  HBM is touched once per cell: read the count row (which
+//    genes are zero), write the E[S] counters.  psi, w, S never exist in HBM (the
+//    reference keeps five L x N fp64/int64 arrays, :216-220,232).
+//  * phase 1 of a sweep, draw_w (:318-323): a rejection sampler.  A warp owns the
+//    32 g genes of its threads as a queue; every trip of the warp loop is ONE attempt
+//    per lane (one Philox block and a fixed amount of arithmetic,
+//    samplers.cuh::pg_attempt) and a lane whose attempt is accepted takes the next
+//    gene of the queue, so neither rejections nor uneven runs leave lanes idle.  The
+//    accepting lane also folds the PREVIOUS sweep's (w, S) into the coeffA/coeffAsq
+//    partials (update_suffStats :245-270 needs w(t) with the kappa/tau drawn after
+//    it) and stores the threshold form of the gene's S draw.
+//  * phase 2, draw_S (:326-342): a sequential scan over the zero genes of a cell
+//    through the running sum_AS.  It is kept EXACT: each update is rewritten as
+//    "s_other > T_i" (samplers.cuh::s_threshold; T_i depends on the uniform only), a
+//    thread scans its own run of g genes assuming the sweep-start sum as its incoming
+//    value and records the smallest |s_other - T_i| it saw (its margin); a block-wide
+//    exclusive scan of the per-thread net changes gives every thread its true
+//    incoming sum; only threads whose incoming sum moved by more than their margin
+//    re-scan (thresholds are in shared memory: three flops per zero gene); repeat to
+//    the fixed point, which is the unique sequential solution.
 //  * draw_kappa_tau (:345-377): five block reductions in fp64, closed-form 2x2
 //    Cholesky draw by one thread, broadcast through shared memory.
-//  * update_suffStats (:245-270) needs w(t) together with the kappa/tau drawn
-//    AFTER it, so the fold of sweep t is deferred into the gene loop of sweep
-//    t+1 (w(t) is still in its slot); per-gene accumulators for coeffA/coeffAsq
-//    are CTA-private (shared memory for small N, an L2-resident scratch row
-//    otherwise) and flushed with fp64 atomics when the CTA changes cell type.
+//  * per-gene accumulators for coeffA/coeffAsq are CTA-private fp32 (shared memory for
+//    small N, an L2-resident scratch row otherwise) and flushed with fp64 atomics
+//    every 16 cells or when the CTA changes cell type.
 #include "common.cuh"
 #include "samplers.cuh"
 #include "sc_shard.h"
