@@ -125,8 +125,11 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def updates_per_step(cfg):
-    return (cfg["L"] * cfg["N"] + cfg["M"] * cfg["N"]) * (cfg["burnin"] + cfg["sample"])
+def updates_per_step(cfg, bulk_mode="gibbs"):
+    sweeps = cfg["burnin"] + cfg["sample"]
+    # the default bulk mode of the CLI is one deterministic mean update per EM iteration
+    bulk = cfg["M"] * cfg["N"] * (sweeps if bulk_mode == "gibbs" else 1)
+    return cfg["L"] * cfg["N"] * sweeps + bulk
 
 
 # ---------------------------------------------------------------------------
@@ -251,7 +254,8 @@ def gpu_main(args, cfg):
 
     def make_gem(**kw):
         return LogitNormalGEM(K=K, G=G, burnin=burnin, sample=sample, thin=1,
-                              bk_mean_approx=False, MLE_CONV=1e-6, MLE_maxiter=args.mle_maxiter,
+                              bk_mean_approx=(args.bulk_mode == "mean"), MLE_CONV=1e-6,
+                              MLE_maxiter=args.mle_maxiter,
                               EM_CONV=1e-6, EM_maxiter=10 ** 6, seed=1, **kw)
 
     gem = make_gem(device_SC=dev_SC, device_BK=dev_BK, L_total=Ll * world, M_total=Ml * world,
@@ -298,7 +302,7 @@ def gpu_main(args, cfg):
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
     dev_ms, wall_ms = float(t[0]), float(t[1])
-    upd_rank = updates_per_step(cfg)
+    upd_rank = updates_per_step(cfg, args.bulk_mode)
     value = upd_rank * world * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: host buffers -> public API -> host results, every step -------------
@@ -370,10 +374,12 @@ def gpu_main(args, cfg):
                     "note": "chain-resident kernel: issue-bound, not HBM-bound (DESIGN.md 4.1)",
                     "updates_per_s_kernel": Ll * N * sweeps / (k_ms * 1e-3)}
     elif bk_ms:
-        alg_bytes = 4.0 * Ml * N * sweeps
+        passes = sweeps if args.bulk_mode == "gibbs" else 2  # mean update: two passes over X
+        alg_bytes = 4.0 * Ml * N * passes
         k_ms = float(np.mean(bk_ms))
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "bk_tile_kernel<2> (all sweeps)",
+        roofline = {"bound": "hbm", "kernel": "bk_split_kernel (all sweeps)" if args.bulk_mode == "gibbs"
+                    else "bk_tile_kernel<KMAX,0/1> (mean update, 2 passes)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
                     "bytes_per_update": 4.0}
@@ -388,7 +394,8 @@ def gpu_main(args, cfg):
         "data": "synthetic (demo_simulate_data.py distributions, generated on device)",
         "config": {"workload": args.workload + ": " + cfg["desc"], "K": K, "N": N,
                    "cells_per_gpu": Ll, "bulk_per_gpu": Ml, "burnin": burnin, "sample": sample,
-                   "thin": 1, "bulk_mode": "gibbs (-no_mean_approx)",
+                   "thin": 1, "bulk_mode": "gibbs (-no_mean_approx)" if args.bulk_mode == "gibbs"
+                   else "mean update (CLI default)",
                    "MLE_maxiter": args.mle_maxiter, "l2": "flushed between steps (256 MiB write)",
                    "parallelism": "cells/bulk samples sharded over %d rank(s)" % world},
         "s_per_em_iter": dev_ms / args.steps / 1e3, "wall_ms_per_step": wall_ms / args.steps,
@@ -411,6 +418,8 @@ def main():
     ap.add_argument("--impl", type=str, default="ursm_b200", choices=["ursm_b200", "reference"])
     ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--mle-maxiter", dest="mle_maxiter", type=int, default=500)
+    ap.add_argument("--bulk-mode", dest="bulk_mode", type=str, default="gibbs",
+                    choices=["gibbs", "mean"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verbose", action="store_true")

@@ -10,7 +10,7 @@
 // so HBM sees X exactly once per pass (4 B per (sample, gene)).
 //   mode 0: numerators of get_nmf_W (:157-164)
 //   mode 1: draw_Z_mean (:149-155) + update_suffStats(1) (:69-78)
-//   mode 2: draw_Z (:132-138), multinomial as a chain of exact binomials
+// (draw_Z (:132-138), the Gibbs mode, is bk_split_kernel below)
 #include "common.cuh"
 #include "samplers.cuh"
 #include "sc_shard.h"
@@ -39,8 +39,38 @@ struct BkTileArgs {
   unsigned int sweep;
 };
 
+// Sums P (a power of two <= 32) values per lane over the 32 lanes of a warp.  Exchange
+// `off` = 16, 8, ...: the lane with that bit set keeps the upper half of its live values
+// and receives the partner's upper half, the other lane the lower halves.  Returns the
+// index of the value whose total ends up in v[0] of this lane (-1 for lanes that hold a
+// duplicate).
+template <int P>
+__device__ __forceinline__ int warp_transpose_reduce(double (&v)[P], int lane) {
+  int idx = 0;
+  int off = 16;
+#pragma unroll
+  for (int c = P / 2; c >= 1; c /= 2) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < c; ++i) {
+      const double send = up ? v[i] : v[i + c];
+      const double recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = (up ? v[i + c] : v[i]) + recv;
+    }
+    if (up) idx += c;
+    off >>= 1;
+  }
+  bool owner = true;
+  for (; off >= 1; off >>= 1) {  // P < 32: the remaining lanes hold partial sums of the same index
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    if (lane & off) owner = false;
+  }
+  return owner ? idx : -1;
+}
+
 template <int KMAX, int MODE>
 __global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
+  constexpr int P = KMAX <= 4 ? 4 : (KMAX <= 8 ? 8 : (KMAX <= 16 ? 16 : 32));
   extern __shared__ double bk_smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int K = a.K, N = a.N;
@@ -49,17 +79,19 @@ __global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
   const int nloc = (int)(j1 - j0);
   double* Wsm = bk_smem;             // [nloc][K] W rows of this CTA's samples
   double* Jsm = bk_smem + nloc * K;  // [nloc][K] CTA-level sums over genes
+  // the thread's A row and its sum_j accumulators live in private shared-memory columns
+  // (registers are needed for the K-wide butterfly below)
+  double* Ar = bk_smem + 2 * a.chunk * K + tid;   // [K][T]
+  double* accI = Ar + K * kBkThreads;              // [K][T]
   for (int t = tid; t < nloc * K; t += kBkThreads) {
     Wsm[t] = a.W[j0 * K + t];
     Jsm[t] = 0.0;
   }
   const int gi = blockIdx.x * kBkThreads + tid;
   const bool in = gi < N;
-  double Ar[KMAX], accI[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    Ar[k] = (k < K && in) ? a.A[(size_t)k * N + gi] : 0.0;
-    accI[k] = 0.0;
+  for (int k = 0; k < K; ++k) {
+    Ar[k * kBkThreads] = in ? a.A[(size_t)k * N + gi] : 0.0;
+    accI[k * kBkThreads] = 0.0;
   }
   __syncthreads();
 
@@ -71,53 +103,36 @@ __global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
     double aw = 0.0;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
-      if (k < K) aw += Wj[k] * Ar[k];
-    if (MODE == 2) {
-      Philox rng(a.key, (uint32_t)gi, (uint32_t)(a.sample_offset + j), kPurposeBulkZ | a.sweep);
-      int rem = active ? (int)xf : 0;
-      double remq = aw;
+      if (k < K) aw += Wj[k] * Ar[k * kBkThreads];
+    const double r = active ? (double)xf / aw : 0.0;
+    double v[P];
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k >= K) break;
-        const double qk = Wj[k] * Ar[k];
-        int z;
-        if (k == K - 1) {
-          z = rem;
-        } else {
-          const double p = fmin(fmax(qk / remq, 0.0), 1.0);
-          z = (rem > 0) ? binomial(rem, p, rng) : 0;
-        }
-        rem -= z;
-        remq -= qk;
-        if (a.accumulate_I) accI[k] += (double)z;
-        const int tot = __reduce_add_sync(0xffffffffu, z);
-        if (lane == 0 && tot != 0) atomicAdd(&Jsm[jl * K + k], (double)tot);
-      }
-    } else {
-      const double r = active ? (double)xf / aw : 0.0;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k >= K) break;
-        double v;
+    for (int k = 0; k < P; ++k) {
+      v[k] = 0.0;
+      if (k < KMAX && k < K) {
         if (MODE == 0) {
-          v = Ar[k] * r;
+          v[k] = Ar[k * kBkThreads] * r;
         } else {
-          v = Wj[k] * Ar[k] * r;
-          accI[k] += v;
+          v[k] = Wj[k] * Ar[k * kBkThreads] * r;
+          accI[k * kBkThreads] += v[k];
         }
-        v = warp_sum(v);
-        if (lane == 0 && v != 0.0) atomicAdd(&Jsm[jl * K + k], v);
       }
     }
+    // sum over the 32 genes of the warp, all K types at once: a butterfly that halves
+    // the number of live values per lane at every exchange (P - 1 + 5 - log2 P shuffles
+    // instead of 5 K); lane `l` ends up with the total of type tr_index(l)
+    const int kk = warp_transpose_reduce<P>(v, lane);
+    if (kk >= 0 && kk < K && v[0] != 0.0) atomicAdd(&Jsm[jl * K + kk], v[0]);
   }
   __syncthreads();
   for (int t = tid; t < nloc * K; t += kBkThreads)
     if (Jsm[t] != 0.0) atomicAdd(&a.sumJ[j0 * K + t], Jsm[t]);
-  if (in && (MODE == 1 || (MODE == 2 && a.accumulate_I))) {
+  if (in && MODE == 1) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (k >= K) break;
-      if (accI[k] != 0.0) atomicAdd(&a.sumI[(size_t)k * N + gi], accI[k] * a.scaleI);
+      const double t = accI[k * kBkThreads];
+      if (t != 0.0) atomicAdd(&a.sumI[(size_t)k * N + gi], t * a.scaleI);
     }
   }
 }
@@ -335,9 +350,9 @@ static void bk_launch_tile(BkShard* b, BkTileArgs& a, cudaStream_t st) {
   a.K = b->K;
   a.sample_offset = b->sample_offset;
   const int gx = (b->N + kBkThreads - 1) / kBkThreads;
-  // enough CTAs to fill the machine a few times over; a chunk's W rows and
-  // per-sample sums (2 x chunk x K doubles) must fit the default 48 KB
-  const long long max_chunk = std::max<long long>(1, (40 * 1024) / (16 * (long long)b->K));
+  // enough CTAs to fill the machine a few times over; a chunk's W rows and per-sample
+  // sums (2 x chunk x K doubles) get 16 KB next to the per-thread columns (2 x K x T doubles)
+  const long long max_chunk = std::max<long long>(1, (16 * 1024) / (16 * (long long)b->K));
   long long want_y = std::max<long long>(1, (long long)(8 * b->num_sms + gx - 1) / gx);
   want_y = std::max<long long>(want_y, (b->M + max_chunk - 1) / max_chunk);
   long long ny = std::min<long long>(b->M, want_y);
@@ -345,18 +360,27 @@ static void bk_launch_tile(BkShard* b, BkTileArgs& a, cudaStream_t st) {
   ny = (b->M + a.chunk - 1) / a.chunk;
   URSM_REQUIRE(ny <= 65535, "bulk tile kernel: too many sample chunks");
   dim3 grid(gx, (unsigned)ny);
-  size_t smem = 2 * (size_t)a.chunk * b->K * sizeof(double);
   const int K = b->K;
+  size_t smem = (2 * (size_t)a.chunk * K + 2 * (size_t)K * kBkThreads) * sizeof(double);
+  URSM_REQUIRE(smem <= 200 * 1024, "bulk tile kernel: too many cell types for shared memory");
+#define URSM_TILE_LAUNCH(KM)                                                                    \
+  do {                                                                                          \
+    if (smem > 48 * 1024)                                                                       \
+      URSM_CUDA(cudaFuncSetAttribute(bk_tile_kernel<KM, MODE>,                                  \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    bk_tile_kernel<KM, MODE><<<grid, kBkThreads, smem, st>>>(a);                                \
+  } while (0)
   if (K <= 4)
-    bk_tile_kernel<4, MODE><<<grid, kBkThreads, smem, st>>>(a);
+    URSM_TILE_LAUNCH(4);
   else if (K <= 8)
-    bk_tile_kernel<8, MODE><<<grid, kBkThreads, smem, st>>>(a);
+    URSM_TILE_LAUNCH(8);
   else if (K <= 12)
-    bk_tile_kernel<12, MODE><<<grid, kBkThreads, smem, st>>>(a);
+    URSM_TILE_LAUNCH(12);
   else if (K <= 20)
-    bk_tile_kernel<20, MODE><<<grid, kBkThreads, smem, st>>>(a);
+    URSM_TILE_LAUNCH(20);
   else
-    bk_tile_kernel<32, MODE><<<grid, kBkThreads, smem, st>>>(a);
+    URSM_TILE_LAUNCH(32);
+#undef URSM_TILE_LAUNCH
   URSM_LAUNCH_CHECK();
 }
 
