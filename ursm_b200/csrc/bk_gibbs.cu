@@ -36,6 +36,7 @@ struct BkTileArgs {
   double scaleI;       // 1/sample
   int accumulate_I;    // mode 2: this sweep is retained
   unsigned long long key;
+  PhiloxKeys rk;       // round keys of `key` (constant-bank operands of the Philox rounds)
   unsigned int sweep;
 };
 
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(kSplitThreads, 3) bk_split_kernel(BkTileArgs a
       if (k == K - 1) {
         z = rem;  // the last type takes what is left
       } else {
-        if ((k & 3) == 0) philox_block(a.key, (uint32_t)gene, jg, ctr2, (uint32_t)(k >> 2), w0, w1, w2, w3);
+        if ((k & 3) == 0) philox_block(a.rk, (uint32_t)gene, jg, ctr2, (uint32_t)(k >> 2), w0, w1, w2, w3);
         const uint32_t wk = (k & 3) == 0 ? w0 : ((k & 3) == 1 ? w1 : ((k & 3) == 2 ? w2 : w3));
         const float qk = Wj[k] * Ar[k * kSplitThreads];
         const double after = fmax(rest - (double)qk, 0.0);
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kSplitThreads, 3) bk_split_kernel(BkTileArgs a
             binom_inv_step(b);
           } else {
             uint32_t e0, e1, e2, e3;
-            philox_block(a.key, (uint32_t)gene, jg, ctr2, 0x100u + (uint32_t)(k << 8) + (uint32_t)extra,
+            philox_block(a.rk, (uint32_t)gene, jg, ctr2, 0x100u + (uint32_t)(k << 8) + (uint32_t)extra,
                          e0, e1, e2, e3);
             ++extra;
             if (b.mode == kBinBtrs) {
@@ -601,6 +602,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned mb = (unsigned)((b->M + 127) / 128);
   const unsigned long long key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1) + 0x5bd1e995ull;
+  const PhiloxKeys rk = philox_keys(key);
   const double inv = 1.0 / sample;
   bk_time_begin(b, st);
   URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_bk_stats_len(bk) * sizeof(double), st));
@@ -625,6 +627,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
     a.scaleI = inv;
     a.accumulate_I = retained ? 1 : 0;
     a.key = key;
+    a.rk = rk;
     a.sweep = (unsigned)sweep;
     bk_launch_split(b, a, st);
     if (!freezeZ) std::swap(b->nA.p, b->nB.p);

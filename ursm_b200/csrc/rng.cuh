@@ -105,26 +105,69 @@ struct Philox {
 // its (c3+1)-th refill in general.  The Gibbs kernel calls this once per sampling
 // ATTEMPT, with c3 = attempt index, so that every lane of a warp executes the
 // generator at full width (no data-dependent refill).
-URSM_HD void philox_block(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+//
+// The round keys are an argument: kernels take a PhiloxKeys by value inside their
+// parameter struct, so every round key is a constant-bank operand of the round's
+// three-input XOR (LOP3 ..., c[0x0][..]) and a round is exactly two IMAD.WIDE.U32 and
+// two LOP3 -- no key-schedule arithmetic in the loop.
+struct PhiloxKeys {
+  uint32_t ka[10], kb[10];
+};
+
+inline PhiloxKeys philox_keys(uint64_t key) {
+  PhiloxKeys k;
+  uint32_t a = (uint32_t)key, b = (uint32_t)(key >> 32);
+  for (int r = 0; r < 10; ++r) {
+    k.ka[r] = a;
+    k.kb[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return k;
+}
+
+URSM_HD void mul_wide(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}"
+      : "=r"(lo), "=r"(hi)
+      : "r"(a), "r"(b));
+#else
+  const uint64_t p = (uint64_t)a * b;
+  lo = (uint32_t)p;
+  hi = (uint32_t)(p >> 32);
+#endif
+}
+
+URSM_HD void philox_block(const PhiloxKeys& k, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                           uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  uint32_t ka = (uint32_t)key, kb = (uint32_t)(key >> 32);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ ka;
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ kb;
-    c1 = (uint32_t)p1;
-    c3 = (uint32_t)p0;
-    c0 = n0;
-    c2 = n2;
-    ka += 0x9E3779B9u;
-    kb += 0xBB67AE85u;
+    uint32_t h0, l0, h1, l1;
+    mul_wide(0xD2511F53u, c0, h0, l0);
+    mul_wide(0xCD9E8D57u, c2, h1, l1);
+    c0 = h1 ^ c1 ^ k.ka[r];
+    c2 = h0 ^ c3 ^ k.kb[r];
+    c1 = l1;
+    c3 = l0;
   }
   r0 = c0;
   r1 = c1;
   r2 = c2;
   r3 = c3;
+}
+
+URSM_HD void philox_block(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                          uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  PhiloxKeys k;
+  uint32_t a = (uint32_t)key, b = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    k.ka[r] = a;
+    k.kb[r] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  philox_block(k, c0, c1, c2, c3, r0, r1, r2, r3);
 }
 
 // Stream "purposes" folded into the third counter word (top 4 bits) so the

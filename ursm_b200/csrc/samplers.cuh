@@ -13,16 +13,43 @@
 
 namespace ursm {
 
-// fast single-precision intrinsics on the device (2-ulp class), libm on the host
+// fast single-precision special functions on the device: the bare MUFU approximations
+// with denormals flushed (ex2/lg2/rcp/rsqrt.approx.ftz, 2-ulp class) -- one MUFU and one
+// multiply each.  The non-ftz forms the __expf/__logf/__fdividef intrinsics compile to
+// without -use_fast_math wrap every MUFU in a denormal-range rescaling (3-4 extra
+// instructions each, ~60 per PG attempt); nothing here needs denormals: every
+// quantity that can underflow is a probability mass that is then exactly 0.  libm on the host.
 #if defined(__CUDA_ARCH__)
-#define URSM_EXPF(x) __expf(x)
-#define URSM_LOGF(x) __logf(x)
-#define URSM_DIV(a, b) __fdividef((a), (b))
-#define URSM_RSQRT(x) rsqrtf(x)
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float mufu_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float mufu_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+#define URSM_EXPF(x) ::ursm::mufu_ex2(1.4426950408889634f * (x))
+#define URSM_LOGF(x) (0.6931471805599453f * ::ursm::mufu_lg2(x))
+#define URSM_DIV(a, b) ((a) * ::ursm::mufu_rcp(b))
+#define URSM_RCP(b) ::ursm::mufu_rcp(b)
+#define URSM_RSQRT(x) ::ursm::mufu_rsqrt(x)
 #else
 #define URSM_EXPF(x) expf(x)
 #define URSM_LOGF(x) logf(x)
 #define URSM_DIV(a, b) ((a) / (b))
+#define URSM_RCP(b) (1.0f / (b))
 #define URSM_RSQRT(x) (1.0f / sqrtf(x))
 #endif
 
@@ -72,15 +99,17 @@ URSM_HD PgTilt pg_tilt(float psi) {
   const float z = 0.5f * fabsf(psi);
   g.hz2 = 0.5f * z * z;
   const float fz = 1.2337005501361697f + g.hz2;
-  g.inv_fz = URSM_DIV(1.0f, fz);
+  g.inv_fz = URSM_RCP(fz);
   g.ig = z >= URSM_PG_INV_T;
   // q/p with the cosh(z) factors cancelled; the exponent is >= 0.008 for every z
   const float ex = g.ig ? (t * fz - z) : (t * fz);
   const float c = g.ig ? 1.2732395447351628f /* 4/pi */ : 0.26903493f /* 2 q0/pi */;
   const float qdivp = c * fz * URSM_EXPF(ex);  // +inf for large z -> mass 0
-  g.mass_right = URSM_DIV(1.0f, 1.0f + qdivp);
-  g.inv_left = URSM_DIV(1.0f, 1.0f - g.mass_right);
-  g.mu = URSM_DIV(1.0f, fmaxf(z, 1e-20f));
+  // mass_right = 1/(1 + q/p); 1/(1 - mass_right) = 1 + p/q (one reciprocal each, no
+  // cancellation)
+  g.mass_right = URSM_RCP(1.0f + qdivp);
+  g.inv_left = 1.0f + URSM_RCP(qdivp);
+  g.mu = URSM_RCP(fmaxf(z, 1e-20f));
   return g;
 }
 

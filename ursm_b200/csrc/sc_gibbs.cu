@@ -54,10 +54,11 @@ struct ScGibbsArgs {
   int burnin, nsweeps, thin, sample;
   int sweep0;           // first sweep index (debug: run sweep `sweep0` only)
   unsigned long long key;
+  PhiloxKeys rk;        // round keys of `key` (constant-bank operands of the Philox rounds)
   unsigned short* cnt;  // [L][N]
   double* cellmom;      // [4][L]
   double* stats;        // coeffA[K][N] | coeffAsq[K][N] | elbo | sk | skk | st | stt
-  float* scratch;       // [grid][2][slots]
+  float* scratch;       // [grid][slots][2]
   int flush_every;
   int* counter;
   int acc_red;          // accumulate the scratch row with reductions (no L1 left)
@@ -92,6 +93,22 @@ __device__ __forceinline__ double block_excl_scan(double v, double* red, double&
 // one run of g genes per lane (phase 2)
 __device__ __forceinline__ int gslot(int i, int pad) { return i + (pad ? (i >> 5) : 0); }
 
+// acc[slot] += (dA, dQ).  Shared memory or an L1-cached scratch row: plain 8-byte
+// read-modify-write (one lane per slot at a time).  L2-resident scratch row and no L1 to
+// speak of (long gene vectors): ONE fire-and-forget vector reduction instead of a
+// load-add-store round trip.
+template <bool ACC_SMEM>
+__device__ __forceinline__ void acc_add(float2* p, float dA, float dQ, int use_red) {
+  if (ACC_SMEM || !use_red) {
+    float2 v = *p;
+    v.x += dA;
+    v.y += dQ;
+    *p = v;
+  } else {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(dA), "f"(dQ) : "memory");
+  }
+}
+
 template <bool ACC_SMEM>
 __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -103,8 +120,9 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
   int* ibc = reinterpret_cast<int*>(bc + 4);                 // [4]
   float* w_s = reinterpret_cast<float*>(ibc + 4);            // [slots] w of the current sweep
   float* T_s = w_s + slots;                                  // [slots] draw_S thresholds
-  float* accA = ACC_SMEM ? (T_s + slots) : (a.scratch + (size_t)blockIdx.x * 2 * slots);
-  float* accQ = accA + slots;
+  // coeffA / coeffAsq partials of gene slot s: acc[s] = (dA, dQ), one 8-byte access
+  float2* acc = reinterpret_cast<float2*>(ACC_SMEM ? (T_s + slots)
+                                                   : (a.scratch + (size_t)blockIdx.x * 2 * slots));
   unsigned short* cnt_s =
       reinterpret_cast<unsigned short*>(ACC_SMEM ? (T_s + 3 * (size_t)slots) : (T_s + slots));
   unsigned char* fl_s = reinterpret_cast<unsigned char*>(cnt_s + slots);
@@ -119,13 +137,11 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
   const int gcount = max(0, min(g, N - i0));
   const int wbase = (tid & ~31) * g;
   const int wtotal = max(0, min(32 * g, N - wbase));
-  const unsigned int lt_mask = (1u << lane) - 1u;
+  unsigned int lt_mask;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
 
   int cur_type = -1, cells_in_acc = 0;
-  for (int s = tid; s < slots; s += T) {
-    accA[s] = 0.f;
-    accQ[s] = 0.f;
-  }
+  for (int s = tid; s < slots; s += T) acc[s] = make_float2(0.f, 0.f);
 
   while (true) {
     __syncthreads();
@@ -139,11 +155,10 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       // flush the CTA-private accumulators into coeffA/coeffAsq[:, cur_type]
       for (int i = tid; i < N; i += T) {
         const int slot = gslot(i, pad);
-        float vA = accA[slot], vQ = accQ[slot];
-        if (vA != 0.f) atomicAdd(&coeffA[(size_t)cur_type * N + i], (double)vA * inv_sample);
-        if (vQ != 0.f) atomicAdd(&coeffQ[(size_t)cur_type * N + i], (double)vQ * inv_sample);
-        accA[slot] = 0.f;
-        accQ[slot] = 0.f;
+        const float2 v = acc[slot];
+        if (v.x != 0.f) atomicAdd(&coeffA[(size_t)cur_type * N + i], (double)v.x * inv_sample);
+        if (v.y != 0.f) atomicAdd(&coeffQ[(size_t)cur_type * N + i], (double)v.y * inv_sample);
+        acc[slot] = make_float2(0.f, 0.f);
       }
       cells_in_acc = 0;
       __syncthreads();
@@ -218,16 +233,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
                 const unsigned int Sp = (fl_s[slot] >> 1) & 1u;
                 const float wold = w_s[slot];
                 const float dA = ((float)Sp - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
-                if (ACC_SMEM || !a.acc_red) {
-                  accA[slot] += dA;
-                  accQ[slot] += dQ;
-                } else {
-                  // L2-resident scratch row and no L1 to speak of (long gene vectors):
-                  // fire-and-forget reductions (one lane per slot at a time, so they are
-                  // uncontended) instead of load-add-store round trips
-                  atomicAdd(&accA[slot], dA);
-                  atomicAdd(&accQ[slot], dQ);
-                }
+                acc_add<ACC_SMEM>(acc + slot, dA, dQ, a.acc_red);
                 cnt_s[slot] += (unsigned short)Sp;
               }
               psi = fmaf(ft, av, fk);
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
           if (!__any_sync(0xffffffffu, active)) break;
           if (active) {
             uint32_t r0, r1, r2, r3;
-            philox_block(a.key, (uint32_t)i, gl, ctr2, (uint32_t)attempt, r0, r1, r2, r3);
+            philox_block(a.rk, (uint32_t)i, gl, ctr2, (uint32_t)attempt, r0, r1, r2, r3);
             if (attempt == 0) rS = r3;  // word 3 of the first attempt: the S uniform
             float x;
             if (pg_attempt(pg, u01(r0), u01(r1), u01(r2), x)) {
@@ -377,13 +383,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
         const unsigned int Sold = (fl_s[slot] >> 1) & 1u;
         const float wold = w_s[slot];
         const float dA = ((float)Sold - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
-        if (ACC_SMEM || !a.acc_red) {
-          accA[slot] += dA;
-          accQ[slot] += dQ;
-        } else {
-          atomicAdd(&accA[slot], dA);
-          atomicAdd(&accQ[slot], dQ);
-        }
+        acc_add<ACC_SMEM>(acc + slot, dA, dQ, a.acc_red);
         cnt_s[slot] += (unsigned short)Sold;
       }
     }
@@ -732,6 +732,7 @@ int ursm_sc_gibbs(ursm_sc* sc, int32_t burnin, int32_t sample, int32_t thin, uin
   a.sample = sample;
   a.sweep0 = 0;
   a.key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1);
+  a.rk = philox_keys(a.key);
   a.stats = d_stats;
   s->sample = sample;
   sc_launch(s, a, st);
@@ -840,6 +841,7 @@ int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kapp
   a.sample = 1;
   a.sweep0 = sweep;
   a.key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1);
+  a.rk = philox_keys(a.key);
   a.stats = stats.p;
   a.S0 = S0.p;
   a.kt0 = kt0.p;
