@@ -73,7 +73,8 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line)."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 10 ms from
+    a thread of this process (nvidia_ml_py), `nvidia-smi -lms` as the fallback."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -81,26 +82,82 @@ class ClockSampler(object):
 
     def __init__(self, index=0):
         self.proc, self.lines, self.index = None, [], index
+        self.nvml, self.thread, self.stop_flag = None, None, False
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except Exception:
+                return self.index
+        return self.index
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                if mx:
+                    self.mx.append(mx)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                    "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons),
+                    "power_w_max": float(max(self.power)) if self.power else None,
+                    "source": "nvml, 10 ms polling during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -122,7 +179,7 @@ class ClockSampler(object):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 def updates_per_step(cfg, bulk_mode="gibbs"):
@@ -323,35 +380,39 @@ def gpu_main(args, cfg):
 
         def e2e_step():
             flush.zero_()
-            # host arrays are this rank's rows: single-process semantics per rank plus the
-            # all-reduce inside the samplers (weak scaling, as in the device-resident arm)
-            g2 = make_gem(SCexpr=nY, BKexpr=nX, init_A=init_A) if world == 1 else None
-            if g2 is None:
-                raise SystemExit("e2e arm is run at N=1 only")
+            # what a user of the reference does per fit: build the model from the host
+            # count matrices (this rank's rows, float64 as np.loadtxt returns them), run
+            # the EM iteration, read every output gem2csv writes back to the host
+            g2 = make_gem(SCexpr=nY, BKexpr=nX, init_A=init_A, local_rows=True,
+                          L_total=Ll * world, M_total=Ml * world,
+                          row_offset_SC=rank * Ll, row_offset_BK=rank * Ml)
             g2.init_gibbs()
             g2.init_mle()
             g2.em_iteration()
             out = [g2.A, g2.alpha if g2.hasBK else None]
-            st = g2.gathered_stats()
+            st = g2.gathered_stats(local=True)
             d2h_box[0] = sum(np.asarray(v).nbytes for v in st.values()) + g2.A.nbytes
             return out, st
 
-        if world == 1:
-            for _ in range(min(args.warmup, 2)):
-                e2e_step()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            n_e2e = max(1, min(args.steps, 3))
-            for _ in range(n_e2e):
-                e2e_step()
-            torch.cuda.synchronize()
-            e2e_s = (time.perf_counter() - t0) / n_e2e
-            e2e = {"value": upd_rank / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                   "d2h_bytes_per_step": int(d2h_box[0]), "ms_per_step": 1e3 * e2e_s,
-                   "steps": n_e2e}
-        else:
-            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                   "note": "e2e arm measured at N=1"}
+        for _ in range(min(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            td.all_reduce(te, op=td.ReduceOp.MAX)
+        e2e_s = float(te[0])
+        e2e = {"value": upd_rank * world / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h_box[0]) * world,
+               "ms_per_step": 1e3 * e2e_s, "steps": n_e2e,
+               "what": "per step and rank: LogitNormalGEM built from pinned host float64 count "
+                       "matrices (upload), one EM iteration, A / alpha / E[S] / E[kappa] / E[tau] "
+                       "/ E[W] / E[Z] read back to host arrays; wall clock, max over ranks"}
 
     if rank != 0:
         if world > 1:
@@ -413,7 +474,7 @@ def gpu_main(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ursm_b200", choices=["ursm_b200", "reference"])
     ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS))

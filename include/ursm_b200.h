@@ -42,6 +42,13 @@ int ursm_version(void);
  * `gpu_launches`), and reset */
 int64_t ursm_launch_count(void);
 void ursm_launch_count_reset(void);
+/* page-locked host blocks for results read back whole (scUnif.py:71 writes exp_S, an
+ * L x N float64 matrix, straight after the fit): cached by size inside the library so a
+ * read-back is one DMA into memory the host never has to fault in.  ursm_host_trim
+ * releases the cache. */
+int ursm_host_alloc(void** out, int64_t bytes);
+int ursm_host_free(void* p);
+int ursm_host_trim(void);
 
 /* ---- single cells: e_step_gibbs.py:171-377 ---------------------------------
  * ursm_sc_create        __init__ :174-197  (caches Y, G, read depths; uploads once)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing export: " + n
         assert n in _lib.SIGNATURES, "unbound in ursm_b200/_lib.py: " + n
     assert set(_lib.SIGNATURES) <= set(names)
-    assert lib.ursm_version() == 100
+    assert lib.ursm_version() == 101
     assert lib.ursm_launch_count() == 0
 
 

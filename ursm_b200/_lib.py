@@ -23,6 +23,9 @@ SIGNATURES = {
     "ursm_version": (c_int, []),
     "ursm_launch_count": (c_i64, []),
     "ursm_launch_count_reset": (None, []),
+    "ursm_host_alloc": (c_int, [PP, c_i64]),
+    "ursm_host_free": (c_int, [c_vp]),
+    "ursm_host_trim": (c_int, []),
     "ursm_sc_create": (c_int, [PP, c_vp, c_vp, c_i64, c_i32, c_i32, c_i64]),
     "ursm_sc_create_dev": (c_int, [PP, c_vp, c_vp, c_i64, c_i32, c_i32, c_i64]),
     "ursm_sc_destroy": (c_int, [c_vp]),
@@ -116,7 +119,47 @@ def i64(a):
 
 def ptr(a):
     """void* of a numpy array (None -> NULL)."""
-    return None if a is None else a.ctypes.data_as(c_vp)
+    return None if a is None else c_vp(a.__array_interface__["data"][0])
+
+
+class PinnedBlock(object):
+    """A page-locked host block from the library's pool, exposed to numpy through the
+    array interface: `np.asarray(block)` is a view that keeps the block alive, and the
+    block goes back to the pool when the last view is gone."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(int(x) for x in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = c_vp()
+        call("ursm_host_alloc", ctypes.byref(p), max(nbytes, 1))
+        self._p = p.value
+        self.__array_interface__ = {"data": (self._p, False), "shape": self.shape,
+                                    "typestr": self.dtype.str, "version": 3}
+
+    def __del__(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p:
+            try:
+                load().ursm_host_free(c_vp(p))
+            except Exception:
+                pass
+
+
+# read-backs up to this size land in pooled page-locked memory; larger ones use
+# ordinary numpy memory (chunked copies)
+PINNED_READBACK_MAX = 1 << 30
+
+
+def host_result(shape, dtype=np.float64):
+    """Uninitialised host array for a device read-back."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if 0 < nbytes <= PINNED_READBACK_MAX:
+        try:
+            return np.asarray(PinnedBlock(shape, dtype))
+        except UrsmError:
+            pass
+    return np.empty(shape, dtype=dtype)
 
 
 def require_cuda():

@@ -437,11 +437,7 @@ static void bk_build_sorted(BkShard* b) {
 }
 
 static void bk_finish_create(BkShard* b) {
-  int dev;
-  URSM_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  URSM_CUDA(cudaGetDeviceProperties(&prop, dev));
-  b->num_sms = prop.multiProcessorCount;
+  b->num_sms = device_sm_count();
   URSM_REQUIRE(b->K <= 32, "bulk kernels support K <= 32 cell types");
   const size_t MK = (size_t)b->M * b->K;
   b->A.alloc((size_t)b->K * b->N);
@@ -477,9 +473,7 @@ int ursm_bk_create(ursm_bk** out, const double* h_X, int64_t M, int32_t N, int32
     const size_t n = (size_t)M * N;
     b->Xown.alloc(n);
     b->X = b->Xown.p;
-    std::vector<float> tmp(n);
-    for (size_t i = 0; i < n; ++i) tmp[i] = (float)h_X[i];
-    URSM_CUDA(cudaMemcpy(b->Xown.p, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    upload_f64_as_f32(h_X, b->Xown.p, n);
     bk_finish_create(b);
   } catch (...) {
     delete b;
@@ -511,6 +505,7 @@ int ursm_bk_create_dev(ursm_bk** out, const float* d_X, int64_t M, int32_t N, in
 
 int ursm_bk_destroy(ursm_bk* bk) {
   URSM_API_BEGIN
+  cudaDeviceSynchronize();  // the pool frees below are ordered on the default stream only
   delete reinterpret_cast<BkShard*>(bk);
   URSM_API_END
 }

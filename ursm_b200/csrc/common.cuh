@@ -58,8 +58,22 @@ struct Failure {
     return 2;                                 \
   }
 
+// Device memory comes from the CUDA stream-ordered pool of the current device with its
+// release threshold raised to "never" (common.cu): a shard that is destroyed and rebuilt
+// -- one per fit in the reference's API -- reuses its blocks instead of paying
+// cudaMalloc/cudaFree (milliseconds each, and a device synchronize) every time.
+// Allocation and release are ordered on the legacy default stream, which every blocking
+// stream synchronizes with; the *_destroy entry points synchronize the device first.
+// attributes of the current device (cudaDeviceGetAttribute: microseconds, where
+// cudaGetDeviceProperties takes milliseconds per call)
+int device_sm_count();
+size_t device_smem_optin();
+
+void* pool_alloc(size_t bytes);
+void pool_free(void* p);
+
 template <class T>
-struct DevBuf {  // owning cudaMalloc buffer
+struct DevBuf {  // owning device buffer
   T* p = nullptr;
   size_t n = 0;
   DevBuf() {}
@@ -68,18 +82,21 @@ struct DevBuf {  // owning cudaMalloc buffer
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) URSM_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    if (count) p = static_cast<T*>(pool_alloc(count * sizeof(T)));
   }
   void zero(cudaStream_t s = 0) {
     if (n) URSM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p);
     p = nullptr;
     n = 0;
   }
   ~DevBuf() { release(); }
 };
+
+// host fp64 matrix -> device fp32 (staged through the device in chunks, cast there; sc_gibbs.cu)
+void upload_f64_as_f32(const double* h, float* d, size_t n);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ double warp_sum(double v) {

@@ -465,11 +465,7 @@ int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t
   m->min_A = min_A;
   try {
     if (m->sc) URSM_REQUIRE(m->sc->N == N && m->sc->K == K, "ursm_mle_create: shard shape mismatch");
-    int dev;
-    URSM_CUDA(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    URSM_CUDA(cudaGetDeviceProperties(&prop, dev));
-    m->num_sms = prop.multiProcessorCount;
+    m->num_sms = device_sm_count();
     const size_t KN = (size_t)K * N;
     m->A.alloc(KN);
     m->Anew.alloc(KN);
@@ -504,6 +500,7 @@ int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t
 
 int ursm_mle_destroy(ursm_mle* mm) {
   URSM_API_BEGIN
+  cudaDeviceSynchronize();  // the pool frees below are ordered on the default stream only
   delete reinterpret_cast<Mle*>(mm);
   URSM_API_END
 }

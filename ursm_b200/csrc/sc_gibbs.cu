@@ -475,7 +475,7 @@ __global__ void cnt_to_f64_kernel(const unsigned short* cnt, double* out, size_t
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-static void upload_f64_as_f32(const double* h, float* d, size_t n) {
+void upload_f64_as_f32(const double* h, float* d, size_t n) {
   // chunked: stage fp64 on the device, cast there
   const size_t chunk = (size_t)1 << 24;
   DevBuf<double> stage;
@@ -490,11 +490,8 @@ static void upload_f64_as_f32(const double* h, float* d, size_t n) {
 }
 
 static void sc_pick_geometry(ScShard* s) {
-  int dev;
-  URSM_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  URSM_CUDA(cudaGetDeviceProperties(&prop, dev));
-  s->num_sms = prop.multiProcessorCount;
+  s->num_sms = device_sm_count();
+  const size_t smem_optin = device_smem_optin();
   int maxT = 1024;
   if (const char* e = getenv("URSM_SC_MAX_THREADS")) maxT = std::max(64, std::min(1024, atoi(e)));
   int gpt = 16;
@@ -506,7 +503,7 @@ static void sc_pick_geometry(ScShard* s) {
   const size_t fixed = 160 * 8 + 4 * 8 + 4 * 4;
   s->pad = 1;
   s->slots = ((s->T * s->g + 31) / 32) * 33 + 32;  // gslot(): one pad word per 32 genes
-  if (fixed + (size_t)s->slots * 11 + 16 > (size_t)prop.sharedMemPerBlockOptin) {
+  if (fixed + (size_t)s->slots * 11 + 16 > smem_optin) {
     s->pad = 0;  // very long gene vectors: give up the padding rather than the residency
     s->slots = s->T * s->g;
   }
@@ -515,7 +512,7 @@ static void sc_pick_geometry(ScShard* s) {
   if (const char* e = getenv("URSM_SC_ACC_SMEM_LIMIT")) acc_limit = atoi(e);
   s->acc_smem = big <= (size_t)acc_limit;
   s->smem = (int)((s->acc_smem ? big : small) + 16);
-  URSM_REQUIRE((size_t)s->smem <= (size_t)prop.sharedMemPerBlockOptin,
+  URSM_REQUIRE((size_t)s->smem <= smem_optin,
                "gene count too large for the chain-resident single-cell kernel "
                "(11 bytes of shared memory per gene)");
   if (s->acc_smem) {
@@ -662,6 +659,7 @@ int ursm_sc_create_dev(ursm_sc** out, const float* d_Y, const int64_t* h_G, int6
 
 int ursm_sc_destroy(ursm_sc* sc) {
   URSM_API_BEGIN
+  cudaDeviceSynchronize();  // the pool frees below are ordered on the default stream only
   delete reinterpret_cast<ScShard*>(sc);
   URSM_API_END
 }

@@ -40,7 +40,7 @@ class DeviceExpS(object):
         self.ndim = 2
 
     def rows(self, lo, hi):
-        out = np.empty((hi - lo, self.shape[1]))
+        out = _lib.host_result((hi - lo, self.shape[1]))
         _lib.call("ursm_sc_get_exp_S", self._sampler._h, _lib.ptr(out), int(lo), int(hi - lo))
         return out
 

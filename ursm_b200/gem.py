@@ -15,7 +15,8 @@ Extras (all optional keyword arguments, absent from the reference):
     to be the FULL problem and each rank keeps the contiguous row block
     `dist.shard_bounds` assigns it; device matrices are taken to be
     the rank's own block, with `L_total` / `M_total` / `row_offset_*` describing
-    the global problem.
+    the global problem.  `local_rows=True` says the same of HOST matrices (each rank
+    passes only its own rows; bench.py's end-to-end arm at N > 1).
 """
 import logging
 
@@ -36,7 +37,7 @@ class LogitNormalGEM(object):
                  burnin=200, sample=200, thin=1, bk_mean_approx=True,
                  MLE_CONV=1e-6, MLE_maxiter=100, EM_CONV=1e-3, EM_maxiter=100,
                  seed=None, device_SC=None, device_BK=None, L_total=None, M_total=None,
-                 row_offset_SC=None, row_offset_BK=None):
+                 row_offset_SC=None, row_offset_BK=None, local_rows=False):
         self.hasBK = BKexpr is not None or device_BK is not None
         self.hasSC = SCexpr is not None or device_SC is not None
         self.K, self.min_A, self.est_alpha = K, min_A, est_alpha
@@ -57,6 +58,11 @@ class LogitNormalGEM(object):
                 self.L = int(L_total) if L_total is not None else self.L_local
                 self._off_SC = int(row_offset_SC or 0)
                 self.SCexpr, self.G = None, G
+            elif local_rows:
+                self.L_local, self.N = SCexpr.shape
+                self.L = int(L_total) if L_total is not None else self.L_local
+                self._off_SC = int(row_offset_SC or 0)
+                self.SCexpr, self.G = SCexpr, G
             else:
                 self.L, self.N = SCexpr.shape
                 lo, hi = dist.shard_bounds(self.L)
@@ -75,6 +81,11 @@ class LogitNormalGEM(object):
                 self.M = int(M_total) if M_total is not None else self.M_local
                 self._off_BK = int(row_offset_BK or 0)
                 self.BKexpr = None
+            elif local_rows:
+                self.M_local, self.N = BKexpr.shape
+                self.M = int(M_total) if M_total is not None else self.M_local
+                self._off_BK = int(row_offset_BK or 0)
+                self.BKexpr = BKexpr
             else:
                 self.M, self.N = BKexpr.shape
                 lo, hi = dist.shard_bounds(self.M)
@@ -269,18 +280,20 @@ class LogitNormalGEM(object):
     # ------------------------------------------------------------------
     # outputs of a sharded run, gathered on every rank (for gem2csv)
     # ------------------------------------------------------------------
-    def gathered_stats(self):
+    def gathered_stats(self, local=False):
         """`suff_stats` entries that `scUnif.gem2csv` writes, with the per-cell /
-        per-sample ones concatenated over ranks in global row order."""
+        per-sample ones concatenated over ranks in global row order (`local=True`: this
+        rank's rows only, no collective)."""
         out = {}
         st = self.suff_stats
+        gather = (lambda a: np.ascontiguousarray(a)) if local else dist.gather_rows
         if self.hasSC:
-            out["exp_S"] = dist.gather_rows(np.asarray(st["exp_S"]))
+            out["exp_S"] = gather(np.asarray(st["exp_S"]))
             for key in ("exp_kappa", "exp_tau", "exp_kappasq", "exp_tausq"):
-                out[key] = dist.gather_rows(st[key].reshape(-1, 1)).reshape(1, -1)
+                out[key] = gather(st[key].reshape(-1, 1)).reshape(1, -1)
         if self.hasBK:
             for key in ("exp_W", "exp_logW"):
-                out[key] = np.ascontiguousarray(dist.gather_rows(st[key].T.copy()).T)
-            out["exp_Zjk"] = dist.gather_rows(st["exp_Zjk"])
+                out[key] = np.ascontiguousarray(gather(st[key].T.copy()).T)
+            out["exp_Zjk"] = gather(st["exp_Zjk"])
             out["exp_Zik"] = st["exp_Zik"]
         return out
