@@ -45,11 +45,11 @@ struct ScGibbsArgs {
   const int* G;         // [L]
   const double* R;      // [L]
   const int* order;     // [L] cells sorted by type
-  const float* A32;     // [K][N] fp32, gene order
+  const float* A32;     // [K][slots] fp32, slot order (gene t g + j at j T + t)
   long long L;
   int N, K;
   long long cell_offset;
-  int g, slots, pad;
+  int g, slots;
   double mu_k, prec_k, mu_t, prec_t;
   int burnin, nsweeps, thin, sample;
   int sweep0;           // first sweep index (debug: run sweep `sweep0` only)
@@ -71,28 +71,6 @@ struct ScGibbsArgs {
   int* rounds_out;          // [L]
 };
 
-__device__ __forceinline__ double block_excl_scan(double v, double* red, double& total) {
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  __syncthreads();
-  if (lane == 31) red[warp] = inc;
-  __syncthreads();
-  double x = (lane < nw) ? red[lane] : 0.0;
-  double pre = warp_sum(lane < warp ? x : 0.0);
-  total = warp_sum(x);
-  return pre + inc - v;
-}
-
-// shared-memory slot of gene i: natural order with one pad word per 32 genes, so that
-// both access patterns are (nearly) conflict free -- consecutive genes (phase 1) and
-// one run of g genes per lane (phase 2)
-__device__ __forceinline__ int gslot(int i, int pad) { return i + (pad ? (i >> 5) : 0); }
-
 // acc[slot] += (dA, dQ).  Shared memory or an L1-cached scratch row: plain 8-byte
 // read-modify-write (one lane per slot at a time).  L2-resident scratch row and no L1 to
 // speak of (long gene vectors): ONE fire-and-forget vector reduction instead of a
@@ -109,34 +87,62 @@ __device__ __forceinline__ void acc_add(float2* p, float dA, float dQ, int use_r
   }
 }
 
+// Shared-memory layout of the per-gene chain state: thread t OWNS the run of genes
+// [t g, (t+1) g) (the unit of the sequential draw_S scan) and gene (t, j) lives in slot
+// j T + t.  Both access patterns are then conflict free without padding: phase 1 walks a
+// warp's genes with consecutive lanes on consecutive owner threads, phase 2 walks a
+// thread's own run with stride T.  The fp32 copy of A^T is stored in the same slot order
+// (ursm_sc_set_params), so its loads are coalesced in both phases.
+__device__ __forceinline__ int slot_of_gene(int i, int g, int T, float inv_g) {
+  int t = (int)((float)i * inv_g);  // i / g for i < 2^22, fixed up below
+  int j = i - t * g;
+  if (j < 0) {
+    --t;
+    j += g;
+  } else if (j >= g) {
+    ++t;
+    j -= g;
+  }
+  return j * T + t;
+}
+
+constexpr int kNormChunk = 64;  // (kappa, tau) normal pairs precomputed per refill
+
 template <bool ACC_SMEM>
 __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = a.g, N = a.N, slots = a.slots, pad = a.pad;
+  const int g = a.g, N = a.N, slots = a.slots, nw = T >> 5;
+  const float inv_g = 1.0f / (float)g;
 
-  double* red = reinterpret_cast<double*>(smem_raw);        // [32*5] reductions
-  double* bc = red + 160;                                    // [4] broadcast
-  int* ibc = reinterpret_cast<int*>(bc + 4);                 // [4]
-  float* w_s = reinterpret_cast<float*>(ibc + 4);            // [slots] w of the current sweep
-  float* T_s = w_s + slots;                                  // [slots] draw_S thresholds
+  double* red = reinterpret_cast<double*>(smem_raw);         // [32]    block_sum scratch
+  double* redA = red + 32;                                    // [2][32] scan: warp totals
+  double* red1 = redA + 64;                                   // [3][32] sum w, w a, w a^2 per warp
+  double* nrm = red1 + 96;                                    // [kNormChunk][2] normal pairs
+  double* bc = nrm + 2 * kNormChunk;                          // [4] broadcast
+  int* redN = reinterpret_cast<int*>(bc + 4);                 // [2][32] scan: warp counts of S
+  int* ibc = redN + 64;                                       // [4]
+  float* w_s = reinterpret_cast<float*>(ibc + 4);             // [slots] w of the current sweep
+  float* T_s = w_s + slots;                                   // [slots] draw_S thresholds
   // coeffA / coeffAsq partials of gene slot s: acc[s] = (dA, dQ), one 8-byte access
   float2* acc = reinterpret_cast<float2*>(ACC_SMEM ? (T_s + slots)
                                                    : (a.scratch + (size_t)blockIdx.x * 2 * slots));
-  unsigned short* cnt_s =
-      reinterpret_cast<unsigned short*>(ACC_SMEM ? (T_s + 3 * (size_t)slots) : (T_s + slots));
-  unsigned char* fl_s = reinterpret_cast<unsigned char*>(cnt_s + slots);
+  unsigned int* Sm_s =
+      reinterpret_cast<unsigned int*>(ACC_SMEM ? (T_s + 3 * (size_t)slots) : (T_s + slots));  // [T]
+  unsigned short* cnt_s = reinterpret_cast<unsigned short*>(Sm_s + T);                       // [slots]
 
   const double inv_sample = 1.0 / (double)a.sample;
   double* coeffA = a.stats;
   double* coeffQ = a.stats + (size_t)a.K * N;
   double* scal = a.stats + 2 * (size_t)a.K * N;
 
-  // this thread's run (phase 2) and this warp's block of genes (phase 1)
+  // this thread's run (phase 2): genes i0 .. i0 + gcount - 1, bit j of the masks below
   const int i0 = tid * g;
   const int gcount = max(0, min(g, N - i0));
-  const int wbase = (tid & ~31) * g;
-  const int wtotal = max(0, min(32 * g, N - wbase));
+  const unsigned int validm = gcount >= 32 ? 0xffffffffu : ((1u << gcount) - 1u);
+  // this warp's queue (phase 1): entry e -> owner thread wfirst + (e & 31), gene j = e >> 5
+  const int wfirst = tid & ~31;
+  const int qtotal = (wfirst * g < N) ? 32 * g : 0;
   unsigned int lt_mask;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
 
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     if (cur_type >= 0 && (finished || type != cur_type || cells_in_acc >= a.flush_every)) {
       // flush the CTA-private accumulators into coeffA/coeffAsq[:, cur_type]
       for (int i = tid; i < N; i += T) {
-        const int slot = gslot(i, pad);
+        const int slot = slot_of_gene(i, g, T, inv_g);
         const float2 v = acc[slot];
         if (v.x != 0.f) atomicAdd(&coeffA[(size_t)cur_type * N + i], (double)v.x * inv_sample);
         if (v.y != 0.f) atomicAdd(&coeffQ[(size_t)cur_type * N + i], (double)v.y * inv_sample);
@@ -170,12 +176,21 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     const unsigned int gl = (unsigned int)(a.cell_offset + l);  // global cell id keys the RNG
     const float Rf = (float)a.R[l];
     const float invR = Rf > 0.f ? 1.0f / Rf : 0.f;
-    const float* Acol = a.A32 + (size_t)type * N;  // A[:, type] in gene order
+    const float* Acol = a.A32 + (size_t)type * slots;  // A[:, type] in SLOT order
 
-    // ---- init_gibbs (:212-225): S ~ Bern(1/2), S[Y>0] = 1, kappa/tau = prior means
+    // ---- init_gibbs (:212-225): S ~ Bern(1/2), S[Y>0] = 1, kappa/tau = prior means.
+    // The count row is read coalesced and staged through w_s; the owner threads then
+    // build their masks: posm (Y > 0) and Sm (the chain's S, one bit per gene).
     for (int i = tid; i < N; i += T) {
-      const int slot = gslot(i, pad);
-      bool pos = a.Y[(size_t)l * N + i] > 0.f;
+      const int slot = slot_of_gene(i, g, T, inv_g);
+      w_s[slot] = a.Y[(size_t)l * N + i];
+      cnt_s[slot] = 0;
+    }
+    __syncthreads();
+    unsigned int posm = 0u, Sm = 0u;
+    for (int j = 0; j < gcount; ++j) {
+      const int i = i0 + j;
+      const unsigned int pos = w_s[j * T + tid] > 0.f ? 1u : 0u;
       unsigned int S;
       if (a.S0) {
         S = a.S0[(size_t)l * N + i] ? 1u : 0u;
@@ -183,19 +198,18 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
         Philox r0(a.key, (uint32_t)i, gl, kPurposeInit);
         S = r0.next() >> 31;
       }
-      if (pos) S = 1u;
-      fl_s[slot] = (unsigned char)((pos ? 1u : 0u) | (S << 1));
-      cnt_s[slot] = 0;
+      posm |= pos << j;
+      Sm |= (S | pos) << j;
     }
-    __syncthreads();
+    const unsigned int zerom = validm & ~posm;  // genes the draw_S scan visits
+    Sm_s[tid] = Sm;
     double kappa = a.kt0 ? a.kt0[l] : a.mu_k;
     double tau = a.kt0 ? a.kt0[a.L + l] : a.mu_t;
     double s_cur;
     {
       double part = 0.0;
-      for (int j = 0; j < gcount; ++j)
-        if (fl_s[gslot(i0 + j, pad)] & 2) part += (double)Acol[i0 + j];
-      s_cur = block_sum(part, red);
+      for (unsigned int m = Sm; m; m &= m - 1u) part += (double)Acol[(__ffs(m) - 1) * T + tid];
+      s_cur = block_sum(part, red);  // (its barriers also order the staging reads above)
     }
 
     double m_k = 0, m_kk = 0, m_t = 0, m_tt = 0, elbo = 0;  // meaningful in thread 0
@@ -208,6 +222,17 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       const float fk = (float)kappa, ft = (float)tau;
       const float cA1 = pt, cA2 = pt * pk, cQ = -0.5f * pt * pt;
       const uint32_t ctr2 = kPurposeGene | (uint32_t)sweep;
+      // the normal pairs of the (kappa, tau) draws depend on (cell, sweep) only: threads
+      // 0 .. kNormChunk-1 precompute a chunk of them off the critical path (the barriers
+      // of this sweep's scan order the writes before thread 0 reads them)
+      const int nrm_idx = (sweep - a.sweep0) % kNormChunk;
+      if (nrm_idx == 0 && tid < kNormChunk && sweep + tid < a.sweep0 + a.nsweeps) {
+        Philox rk(a.key, 0xffffffffu, gl, kPurposeCell | (uint32_t)(sweep + tid));
+        double n0, n1;
+        normal_pair(rk, n0, n1);
+        nrm[2 * tid] = n0;
+        nrm[2 * tid + 1] = n1;
+      }
       double sw = 0, swa = 0, swaa = 0;
       // ---- phase 1: draw_w (:318-323), the deferred update_suffStats fold and the
       // draw_S thresholds, for the 32 g genes of this warp in ANY order.  Every trip
@@ -224,26 +249,31 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
           const unsigned int free_mask = __ballot_sync(0xffffffffu, need);
           if (need) {
             const int e = cursor + __popc(free_mask & lt_mask);
-            need = false;
-            if (e < wtotal) {
-              i = wbase + e;
-              slot = gslot(i, pad);
-              av = Acol[i];
-              if (prev_ret) {  // update_suffStats (:245-270) of the previous sweep
-                const unsigned int Sp = (fl_s[slot] >> 1) & 1u;
-                const float wold = w_s[slot];
-                const float dA = ((float)Sp - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
-                acc_add<ACC_SMEM>(acc + slot, dA, dQ, a.acc_red);
-                cnt_s[slot] += (unsigned short)Sp;
+            if (e < qtotal) {
+              const int to = wfirst + (e & 31), j = e >> 5;
+              i = to * g + j;
+              if (i < N) {
+                need = false;
+                slot = j * T + to;
+                av = Acol[slot];
+                if (prev_ret) {  // update_suffStats (:245-270) of the previous sweep
+                  const unsigned int Sp = (Sm_s[to] >> j) & 1u;
+                  const float wold = w_s[slot];
+                  const float dA = ((float)Sp - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
+                  acc_add<ACC_SMEM>(acc + slot, dA, dQ, a.acc_red);
+                  cnt_s[slot] += (unsigned short)Sp;
+                }
+                psi = fmaf(ft, av, fk);
+                pg = pg_tilt(psi);
+                attempt = 0;
+                active = true;
               }
-              psi = fmaf(ft, av, fk);
-              pg = pg_tilt(psi);
-              attempt = 0;
-              active = true;
+            } else {
+              need = false;  // queue exhausted: this lane is done for the sweep
             }
           }
           cursor += __popc(free_mask);
-          if (!__any_sync(0xffffffffu, active)) break;
+          if (!__any_sync(0xffffffffu, active || need)) break;
           if (active) {
             uint32_t r0, r1, r2, r3;
             philox_block(a.rk, (uint32_t)i, gl, ctr2, (uint32_t)attempt, r0, r1, r2, r3);
@@ -265,100 +295,100 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
           }
         }
       }
+      sw = warp_sum(sw);
+      swa = warp_sum(swa);
+      swaa = warp_sum(swaa);
+      if (lane == 0) {
+        red1[warp] = sw;
+        red1[32 + warp] = swa;
+        red1[64 + warp] = swaa;
+      }
       __syncwarp();  // phase 2 reads what other lanes of this warp wrote
       // ---- phase 2: draw_S (:326-342), the in-cell sequential scan, kept EXACT:
-      // every thread scans its own run from the sweep-start sum (speculation), a block
-      // scan of the net changes gives the true incoming sums, threads whose incoming
-      // sum moved by more than their margin re-scan (thresholds are in shared memory,
-      // so a re-scan is three flops per zero gene), to the fixed point.
-      double as = 0, s_run = s_cur, used_in = s_cur;
-      int nS = 0;
+      // every thread scans the zero genes of its own run from the sweep-start sum
+      // (speculation), a block scan of the net changes gives the true incoming sums,
+      // threads whose incoming sum moved by more than their margin re-scan (thresholds
+      // are in shared memory, so a re-scan is a handful of flops per zero gene), to the
+      // fixed point.  S lives in a register bit mask per owner thread.
+      double s_run = s_cur, used_in = s_cur, total = 0.0;
+      unsigned int Snew_m = Sm;
       float margin = INFINITY;
       bool scan = true;
       int rounds = 0;
       while (true) {
         if (scan) {
           margin = INFINITY;
-          nS = 0;
-          as = 0;
           s_run = used_in;
-          for (int j = 0; j < gcount; ++j) {
-            const int slot = gslot(i0 + j, pad);
-            const unsigned int f = fl_s[slot];
-            // bit 1 = S of this sweep so far, bit 2 = S at the start of the sweep
-            const unsigned int pos = f & 1u;
-            const unsigned int Sold = (rounds == 0) ? ((f >> 1) & 1u) : ((f >> 2) & 1u);
-            const double ad = (double)Acol[i0 + j];
-            unsigned int Snew = 1u;
-            if (!pos) {
-              const double Tth = (double)T_s[slot];
-              const double so = s_run - (Sold ? ad : 0.0);
-              Snew = (so > Tth) ? 1u : 0u;
-              margin = fminf(margin, fabsf((float)(so - Tth)));
-              s_run = so + (Snew ? ad : 0.0);
-            }
-            fl_s[slot] = (unsigned char)(pos | (Snew << 1) | (Sold << 2));
-            nS += (int)Snew;
-            if (Snew) as += ad;
+          Snew_m = Sm;
+          for (unsigned int m = zerom; m; m &= m - 1u) {
+            const int j = __ffs(m) - 1;
+            const double ad = (double)Acol[j * T + tid];
+            const double Tth = (double)T_s[j * T + tid];
+            const double so = s_run - (((Sm >> j) & 1u) ? ad : 0.0);
+            const bool on = so > Tth;
+            margin = fminf(margin, fabsf((float)(so - Tth)));
+            s_run = so + (on ? ad : 0.0);
+            Snew_m = on ? (Snew_m | (1u << j)) : (Snew_m & ~(1u << j));
           }
         }
-        double total;
+        // block-wide exclusive scan of the net changes (double-buffered warp totals)
         const double delta = s_run - used_in;
-        const double incoming = s_cur + block_excl_scan(delta, red, total);
+        double inc = delta;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const int buf = (rounds & 1) * 32;
+        const int nSw = __reduce_add_sync(0xffffffffu, __popc(Snew_m & validm));
+        if (lane == 31) redA[buf + warp] = inc;
+        if (lane == 0) redN[buf + warp] = nSw;
+        __syncthreads();
+        const double x = (lane < nw) ? redA[buf + lane] : 0.0;
+        const double pre = warp_sum(lane < warp ? x : 0.0);
+        total = warp_sum(x);
+        const double incoming = s_cur + pre + inc - delta;
         const bool viol = !(fabs(incoming - used_in) < (double)margin) && incoming != used_in &&
                           margin != INFINITY;
-        if (!__syncthreads_or(viol) || rounds > T) break;
+        if (!__syncthreads_or(viol) || rounds > T) {
+          // ---- draw_kappa_tau (:345-377): warp 0 sums the per-warp partials, one thread
+          // solves the 2x2 system and draws from the precomputed normal pair
+          if (warp == 0) {
+            double x0 = (lane < nw) ? red1[lane] : 0.0;
+            double x1 = (lane < nw) ? red1[32 + lane] : 0.0;
+            double x2 = (lane < nw) ? red1[64 + lane] : 0.0;
+            int x4 = (lane < nw) ? redN[buf + lane] : 0;
+            x0 = warp_sum(x0);
+            x1 = warp_sum(x1);
+            x2 = warp_sum(x2);
+            x4 = warp_sum(x4);
+            if (lane == 0) {
+              const double x3 = s_cur + total;  // sum_AS after this sweep's S draws
+              const double d0 = x0 + a.prec_k, d1 = x2 + a.prec_t, off = x1;
+              const double det = d0 * d1 - off * off;
+              const double c00 = d1 / det, c01 = -off / det, c11 = d0 / det;
+              const double b0 = (double)x4 - 0.5 * N + a.mu_k * a.prec_k;
+              const double b1 = x3 - 0.5 + a.mu_t * a.prec_t;
+              const double m0 = c00 * b0 + c01 * b1, m1 = c01 * b0 + c11 * b1;
+              const double l00 = sqrt(c00), l10 = c01 / l00;
+              const double l11 = sqrt(fmax(c11 - l10 * l10, 0.0));
+              const double n0 = nrm[2 * nrm_idx], n1 = nrm[2 * nrm_idx + 1];
+              bc[0] = m0 + l00 * n0;
+              bc[1] = m1 + l10 * n0 + l11 * n1;
+              bc[2] = x3;
+              bc[3] = x0;  // sum_i w
+              ibc[1] = x4;
+            }
+          }
+          break;
+        }
         ++rounds;
         scan = viol;
         if (viol) used_in = incoming;
       }
       rounds_total += rounds;
-      // ---- draw_kappa_tau (:345-377)
-      sw = warp_sum(sw);
-      swa = warp_sum(swa);
-      swaa = warp_sum(swaa);
-      as = warp_sum(as);
-      nS = warp_sum(nS);
-      const int nw = T >> 5;
-      __syncthreads();
-      if (lane == 0) {
-        red[warp] = sw;
-        red[32 + warp] = swa;
-        red[64 + warp] = swaa;
-        red[96 + warp] = as;
-        red[128 + warp] = (double)nS;
-      }
-      __syncthreads();
-      if (warp == 0) {
-        double x0 = (lane < nw) ? red[lane] : 0.0;
-        double x1 = (lane < nw) ? red[32 + lane] : 0.0;
-        double x2 = (lane < nw) ? red[64 + lane] : 0.0;
-        double x3 = (lane < nw) ? red[96 + lane] : 0.0;
-        double x4 = (lane < nw) ? red[128 + lane] : 0.0;
-        x0 = warp_sum(x0);
-        x1 = warp_sum(x1);
-        x2 = warp_sum(x2);
-        x3 = warp_sum(x3);
-        x4 = warp_sum(x4);
-        if (lane == 0) {
-          const double d0 = x0 + a.prec_k, d1 = x2 + a.prec_t, off = x1;
-          const double det = d0 * d1 - off * off;
-          const double c00 = d1 / det, c01 = -off / det, c11 = d0 / det;
-          const double b0 = x4 - 0.5 * N + a.mu_k * a.prec_k;
-          const double b1 = x3 - 0.5 + a.mu_t * a.prec_t;
-          const double m0 = c00 * b0 + c01 * b1, m1 = c01 * b0 + c11 * b1;
-          const double l00 = sqrt(c00), l10 = c01 / l00;
-          const double l11 = sqrt(fmax(c11 - l10 * l10, 0.0));
-          Philox rk(a.key, 0xffffffffu, gl, kPurposeCell | (uint32_t)sweep);
-          double n0, n1;
-          normal_pair(rk, n0, n1);
-          bc[0] = m0 + l00 * n0;
-          bc[1] = m1 + l10 * n0 + l11 * n1;
-          bc[2] = x3;  // exact sum_AS for the next sweep
-          bc[3] = x0;  // sum_i w
-          ibc[1] = (int)x4;
-        }
-      }
+      Sm = Snew_m;
+      Sm_s[tid] = Sm;  // read by this warp's lanes in the next sweep's fold
       __syncthreads();
       kappa = bc[0];
       tau = bc[1];
@@ -375,12 +405,12 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       pk = (float)kappa;
       pt = (float)tau;
     }
-    // ---- fold of the last sweep, write-back
+    // ---- fold of the last sweep (owner threads, own runs), write-back
     if (prev_ret) {
       const float cA1 = pt, cA2 = pt * pk, cQ = -0.5f * pt * pt;
       for (int j = 0; j < gcount; ++j) {
-        const int slot = gslot(i0 + j, pad);
-        const unsigned int Sold = (fl_s[slot] >> 1) & 1u;
+        const int slot = j * T + tid;
+        const unsigned int Sold = (Sm >> j) & 1u;
         const float wold = w_s[slot];
         const float dA = ((float)Sold - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
         acc_add<ACC_SMEM>(acc + slot, dA, dQ, a.acc_red);
@@ -389,10 +419,13 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     }
     __syncthreads();
     for (int i = tid; i < N; i += T) {
-      const int slot = gslot(i, pad);
+      const int slot = slot_of_gene(i, g, T, inv_g);
       a.cnt[(size_t)l * N + i] = cnt_s[slot];
       if (a.w_out) a.w_out[(size_t)l * N + i] = w_s[slot];
-      if (a.S_out) a.S_out[(size_t)l * N + i] = (fl_s[slot] >> 1) & 1u;
+      if (a.S_out) {
+        const int to = slot % T, j = slot / T;
+        a.S_out[(size_t)l * N + i] = (Sm_s[to] >> j) & 1u;
+      }
     }
     if (tid == 0) {
       a.cellmom[l] = m_k * inv_sample;
@@ -500,21 +533,21 @@ static void sc_pick_geometry(ScShard* s) {
   T = std::max(64, std::min(maxT / 32 * 32, T));
   s->T = T;
   s->g = (s->N + T - 1) / T;
-  const size_t fixed = 160 * 8 + 4 * 8 + 4 * 4;
-  s->pad = 1;
-  s->slots = ((s->T * s->g + 31) / 32) * 33 + 32;  // gslot(): one pad word per 32 genes
-  if (fixed + (size_t)s->slots * 11 + 16 > smem_optin) {
-    s->pad = 0;  // very long gene vectors: give up the padding rather than the residency
-    s->slots = s->T * s->g;
-  }
-  size_t small = fixed + (size_t)s->slots * 11, big = fixed + (size_t)s->slots * 19;
+  URSM_REQUIRE(s->g <= 32, "gene count too large for the chain-resident single-cell kernel "
+                           "(at most 32 genes per thread)");
+  // reductions / broadcast / normal pairs, then per gene slot 10 bytes (w, threshold,
+  // E[S] counter) + 8 for in-smem accumulators, and one S bit mask per thread
+  const size_t fixed = (32 + 64 + 96 + 2 * kNormChunk + 4) * 8 + (64 + 4) * 4 + (size_t)s->T * 4;
+  s->pad = 0;
+  s->slots = s->T * s->g;
+  size_t small = fixed + (size_t)s->slots * 10, big = fixed + (size_t)s->slots * 18;
   int acc_limit = 32 * 1024;
   if (const char* e = getenv("URSM_SC_ACC_SMEM_LIMIT")) acc_limit = atoi(e);
   s->acc_smem = big <= (size_t)acc_limit;
   s->smem = (int)((s->acc_smem ? big : small) + 16);
   URSM_REQUIRE((size_t)s->smem <= smem_optin,
                "gene count too large for the chain-resident single-cell kernel "
-               "(11 bytes of shared memory per gene)");
+               "(10 bytes of shared memory per gene)");
   if (s->acc_smem) {
     URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem));
@@ -564,7 +597,7 @@ static void sc_finish_create(ScShard* s, const int64_t* h_G) {
   s->counter.alloc(1);
   s->A.alloc((size_t)s->N * s->K);
   sc_pick_geometry(s);
-  s->Aslot.alloc((size_t)s->K * s->N);
+  s->Aslot.alloc((size_t)s->K * s->slots);
   s->sample = 1;
   URSM_CUDA(cudaDeviceSynchronize());
 }
@@ -581,7 +614,6 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
   a.cell_offset = s->cell_offset;
   a.g = s->g;
   a.slots = s->slots;
-  a.pad = s->pad;
   a.mu_k = s->pkappa[0];
   a.prec_k = 1.0 / s->pkappa[1];
   a.mu_t = s->ptau[0];
@@ -697,9 +729,12 @@ int ursm_sc_set_params(ursm_sc* sc, const double* h_A, const double* h_pkappa,
   URSM_REQUIRE(h_pkappa[1] > 0 && h_ptau[1] > 0, "ursm_sc_set_params: prior variance must be > 0");
   const int N = s->N, K = s->K;
   URSM_CUDA(cudaMemcpy(s->A.p, h_A, (size_t)N * K * sizeof(double), cudaMemcpyHostToDevice));
-  std::vector<float> slot((size_t)K * N, 0.f);  // A^T in fp32, gene order
+  // A^T in fp32, in the kernel's SLOT order: gene i = t g + j sits at j T + t
+  std::vector<float> slot((size_t)K * s->slots, 0.f);
   for (int k = 0; k < K; ++k)
-    for (int i = 0; i < N; ++i) slot[(size_t)k * N + i] = (float)h_A[(size_t)i * K + k];
+    for (int i = 0; i < N; ++i)
+      slot[(size_t)k * s->slots + (size_t)(i % s->g) * s->T + i / s->g] =
+          (float)h_A[(size_t)i * K + k];
   URSM_CUDA(cudaMemcpy(s->Aslot.p, slot.data(), slot.size() * sizeof(float),
                        cudaMemcpyHostToDevice));
   s->pkappa[0] = h_pkappa[0];
