@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
 // ---------------------------------------------------------------------------
 constexpr int kSplitThreads = 256;
 
-__global__ void __launch_bounds__(kSplitThreads, 3) bk_split_kernel(BkTileArgs a) {
+__global__ void __launch_bounds__(kSplitThreads, 4) bk_split_kernel(BkTileArgs a) {
   extern __shared__ __align__(16) unsigned char split_smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int K = a.K, N = a.N;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kSplitThreads, 3) bk_split_kernel(BkTileArgs a
         int extra = 0;  // further Philox blocks of this item: BTRS attempts, inversion restarts
         while (b.mode != kBinDone) {
           if (b.mode == kBinInv) {
-            binom_inv_step(b);
+            binom_inv_chunk4(b);
           } else {
             uint32_t e0, e1, e2, e3;
             philox_block(a.rk, (uint32_t)gene, jg, ctr2, 0x100u + (uint32_t)(k << 8) + (uint32_t)extra,

@@ -420,42 +420,30 @@ URSM_HD void binom_begin(BinomState& b, int n, float p, float pc, float u) {
   }
 }
 
-// up to `steps` CDF steps; kBinDone when u falls inside the current atom, kBinRetry
-// when the search ran past the guard bound (rounding deficit of the fp32 pmf sum).
-// pmf(x)/pmf(x-1) = (n-x+1) s / x = c/x - s.
-URSM_HD void binom_inv_steps(BinomState& b, int steps) {
-  for (int it = 0; it < steps; ++it) {
-    if (b.mode != kBinInv) break;
-    if (b.u <= b.px) {
-      b.result = b.flip ? b.n - b.x : b.x;
-      b.mode = kBinDone;
-      break;
+// pmf(x)/pmf(x-1) = (n-x+1) s / x = c/x - s.  kBinDone when u falls inside the current
+// atom, kBinRetry when the search ran past the guard bound (rounding deficit of the fp32
+// pmf sum).
+// Four CDF steps as straight-line predicated code (the kernel's inner loop): no exit test,
+// mode test or branch per step -- a lane that has landed just stops advancing.  The guard
+// bound is checked once per chunk (a lane can overrun it by at most three atoms, which
+// are legitimate atoms of the same inversion; beyond n the pmf is <= 0 and nothing lands).
+URSM_HD void binom_inv_chunk4(BinomState& b) {
+  bool landed = false;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    landed = landed || (b.u <= b.px);
+    if (!landed) {
+      b.u -= b.px;
+      ++b.x;
+      b.px *= fmaf(b.c, URSM_RCP((float)b.x), -b.s);
     }
-    b.u -= b.px;
-    ++b.x;
-    if (b.x > b.bound) {
-      b.mode = kBinRetry;
-      break;
-    }
-    b.px *= fmaf(b.c, URSM_DIV(1.0f, (float)b.x), -b.s);
   }
-}
-
-// a single CDF step (the kernel drives these with a warp vote so a chunk ends as soon
-// as every lane of the warp has landed)
-URSM_HD void binom_inv_step(BinomState& b) {
-  if (b.u <= b.px) {
+  if (landed) {
     b.result = b.flip ? b.n - b.x : b.x;
     b.mode = kBinDone;
-    return;
-  }
-  b.u -= b.px;
-  ++b.x;
-  if (b.x > b.bound) {
+  } else if (b.x > b.bound) {
     b.mode = kBinRetry;
-    return;
   }
-  b.px *= fmaf(b.c, URSM_DIV(1.0f, (float)b.x), -b.s);
 }
 
 URSM_HD float btrs_fc(int k) {  // Stirling series tail: log(k!) - Stirling's formula
@@ -531,7 +519,7 @@ URSM_HD int binomial_f32(int n, float p, float pc, RNG& rng) {
   binom_begin(b, n, p, pc, rng.uniform());
   for (int guard = 0; guard < 100000 && b.mode != kBinDone; ++guard) {
     if (b.mode == kBinInv) {
-      binom_inv_steps(b, 8);
+      binom_inv_chunk4(b);
     } else if (b.mode == kBinBtrs) {
       const float U = rng.uniform(), V = rng.uniform();
       binom_btrs_attempt(b, U, V);
