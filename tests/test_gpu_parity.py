@@ -340,3 +340,40 @@ def test_degenerate_sizes(ub):
     eS = np.asarray(gem.suff_stats["exp_S"])
     assert eS.shape == (1, 33) and np.all(eS[Y > 0] == 1)
     np.testing.assert_allclose(gem.suff_stats["exp_Zjk"].sum(), X.sum(), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# E[S] counter width: one byte per entry when sample <= 255, two otherwise -- the
+# chains and everything the M-step derives from the counters must not depend on it
+# (ragged N: the 8-byte vector loads fall back to the scalar path)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [96, 101])
+def test_counter_width_does_not_change_results(ub, N, monkeypatch):
+    K, L = 3, 40
+    sim = orc.simulate(N=N, K=K, L=L, M=0, seed=11)
+    Y, G = sim["Y"], sim["G"]
+    itype = _itype(G, K)
+    A = orc.init_A(Y, None, K, itype, 1e-6)
+    pk, pt = np.array([-1., 0.01]), np.array([N, 0.01 * N], dtype=float)
+    res = {}
+    for width in (1, 2):
+        if width == 2:
+            monkeypatch.setenv("URSM_SC_CNT16", "1")
+        else:
+            monkeypatch.delenv("URSM_SC_CNT16", raising=False)
+        sc = ub.es.LogitNormalGibbs_SC(A, pk, pt, Y, G, itype, seed=77)
+        sc.gibbs(burnin=3, sample=9, thin=1)
+        eS = np.asarray(sc.suff_stats["exp_S"]).copy()
+        mle = ub.ms.LogitNormalMLE(None, Y, G, K, itype, False, True, A, None, pk, pt, 1e-6, 1,
+                                   1e-6, 5)
+        mle.update_suff_stats(dict(sc.suff_stats))
+        elbo = mle.compute_elbo()
+        mle.opt_A_u()
+        res[width] = (eS, np.copy(mle.gd_coeffAinv), np.copy(mle.gd_coeffConst), np.copy(mle.u),
+                      elbo, np.copy(mle.A))
+    monkeypatch.delenv("URSM_SC_CNT16", raising=False)
+    np.testing.assert_array_equal(res[1][0], res[2][0])
+    assert set(np.unique(np.round(res[1][0] * 9))) <= set(range(10))
+    for a, b in zip(res[1][1:5], res[2][1:5]):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(res[1][5], res[2][5], rtol=1e-6, atol=1e-12)

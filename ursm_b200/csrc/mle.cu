@@ -29,7 +29,7 @@ struct Mle {
   const double* cAinv = nullptr;         // [K][N] caller-owned (all-reduced)
   const double* cA = nullptr;
   const double* coeffA = nullptr;
-  DevBuf<double> u, ratio;               // [L] u_l and R_l / u_l
+  DevBuf<double> u, ratio;               // [L] u_l; partial sums of the u pass (u_acc)
   DevBuf<int> act_cur, act_next;         // [K] columns in opt_Ak at the start / end of an iteration
   DevBuf<int> niter, base, halv, win;    // [K] outer iterations, halvings already tried, total halvings
   DevBuf<double> cand;                   // [K][kCand][N] candidate columns of one backtracking batch
@@ -45,150 +45,220 @@ constexpr int kCand = 16;  // trial step sizes of backtracking evaluated concurr
 
 constexpr int kColThreads = 256;
 
-// MODE 0: out[type][i] += Y_li * E[S_li]            (m_step.py:88-89)
-// MODE 1: out[type][i] += E[S_li] * R_l / u_l       (m_step.py:123-125), active types only
-// A thread owns four adjacent genes (one 64-bit load of counters per cell) and walks a
-// chunk of the type-sorted cells, four cells per trip so that four independent loads
-// are in flight; `ratio` = R_l/u_l comes from mle_u_kernel.  HBM-bound: 2 B per
-// cell x gene (MODE 0 adds the 4 B count).
-constexpr int kColGenes = 4;
-
-template <int MODE>
-__global__ void __launch_bounds__(kColThreads)
-mle_colsum_kernel(const float* Y, const unsigned short* cnt, const int* G, const int* order,
-                  const double* ratio, const int* active, long long L, int N, int chunk,
-                  double inv_sample, double* out) {
-  const int i = kColGenes * (blockIdx.x * kColThreads + threadIdx.x);
-  const long long c0 = (long long)blockIdx.y * chunk, c1 = min(L, c0 + chunk);
-  if (i >= N) return;
-  const bool vec = (i + 3 < N) && ((N & 3) == 0);  // 64-bit loads need 8-byte aligned rows
-  double acc[kColGenes] = {0.0, 0.0, 0.0, 0.0};
-  int cur = -1;
-  auto flush = [&]() {
-    if (cur < 0) return;
-#pragma unroll
-    for (int q = 0; q < kColGenes; ++q)
-      if (acc[q] != 0.0 && i + q < N) atomicAdd(&out[(size_t)cur * N + i + q], acc[q]);
-#pragma unroll
-    for (int q = 0; q < kColGenes; ++q) acc[q] = 0.0;
-  };
-  auto load4 = [&](int l, unsigned int& lo, unsigned int& hi) {
-    const unsigned short* row = cnt + (size_t)l * N + i;
-    if (vec) {
-      const uint2 v = *reinterpret_cast<const uint2*>(row);
-      lo = v.x;
-      hi = v.y;
-    } else {
-      lo = row[0];
-      hi = 0u;
-      if (i + 1 < N) lo |= (unsigned int)row[1] << 16;
-      if (i + 2 < N) hi = row[2];
-      if (i + 3 < N) hi |= (unsigned int)row[3] << 16;
-    }
-  };
-  for (long long c = c0; c < c1; c += 4) {
-    int l[4], ty[4];
-    unsigned int lo[4], hi[4];
-    double w[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const bool ok = c + q < c1;
-      l[q] = ok ? order[c + q] : -1;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      ty[q] = l[q] >= 0 ? G[l[q]] : -1;
-      const bool use = ty[q] >= 0 && (MODE == 0 || active[ty[q]]);
-      if (!use) ty[q] = ty[q] >= 0 ? -2 - ty[q] : -1;  // keep the type for flushing, skip the row
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      lo[q] = hi[q] = 0u;
-      w[q] = 0.0;
-      if (ty[q] >= 0) {
-        load4(l[q], lo[q], hi[q]);
-        w[q] = (MODE == 1) ? ratio[l[q]] * inv_sample : inv_sample;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (l[q] < 0) continue;
-      const int type = ty[q] >= 0 ? ty[q] : -2 - ty[q];
-      if (type != cur) {
-        flush();
-        cur = type;
-      }
-      if (ty[q] < 0) continue;
-      const double e0 = (double)(lo[q] & 0xffffu), e1 = (double)(lo[q] >> 16);
-      const double e2 = (double)(hi[q] & 0xffffu), e3 = (double)(hi[q] >> 16);
-      if (MODE == 0) {
-        const float* y = Y + (size_t)l[q] * N + i;
-        acc[0] += (double)y[0] * e0 * w[q];
-        if (i + 1 < N) acc[1] += (double)y[1] * e1 * w[q];
-        if (i + 2 < N) acc[2] += (double)y[2] * e2 * w[q];
-        if (i + 3 < N) acc[3] += (double)y[3] * e3 * w[q];
-      } else {
-        acc[0] += e0 * w[q];
-        acc[1] += e1 * w[q];
-        acc[2] += e2 * w[q];
-        acc[3] += e3 * w[q];
-      }
-    }
-  }
-  flush();
+// small unsigned integer -> double without the (quarter-rate) I2F.F64: put it in the low
+// mantissa word of 2^52 and subtract 2^52 (one DADD)
+__device__ __forceinline__ double small_uint_to_double(unsigned int c) {
+  return __hiloint2double(0x43300000, (int)c) - 4503599627370496.0;
 }
 
-// u_l = sum_i A[i, G_l] E[S_li] and ratio_l = R_l / u_l  (one warp per cell; active types)
-__global__ void mle_u_kernel(const unsigned short* cnt, const int* G, const double* A,
-                             const double* R, const int* active, long long L, int N,
-                             double inv_sample, double* u, double* ratio) {
-  const long long l = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (l >= L) return;
-  const int type = G[l];
-  if (!active[type]) return;
-  const double* Ak = A + (size_t)type * N;
-  const unsigned short* row = cnt + (size_t)l * N;
-  double s = 0.0;
-  if ((N & 3) == 0) {  // 64-bit loads: four counters per lane and trip
-    const uint2* row4 = reinterpret_cast<const uint2*>(row);
-    const int n4 = N >> 2;
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int q = lane; q < n4; q += 128) {  // four independent 8-byte loads in flight
-      const uint2 z = make_uint2(0u, 0u);
-      const int q1 = q + 32, q2 = q + 64, q3 = q + 96;
-      const uint2 c0 = row4[q];
-      const uint2 c1 = q1 < n4 ? row4[q1] : z;
-      const uint2 c2 = q2 < n4 ? row4[q2] : z;
-      const uint2 c3 = q3 < n4 ? row4[q3] : z;
-      const double* a0 = Ak + 4 * q;
-      s += a0[0] * (double)(c0.x & 0xffffu) + a0[1] * (double)(c0.x >> 16) +
-           a0[2] * (double)(c0.y & 0xffffu) + a0[3] * (double)(c0.y >> 16);
-      if (q1 < n4) {
-        const double* a1 = Ak + 4 * q1;
-        s1 += a1[0] * (double)(c1.x & 0xffffu) + a1[1] * (double)(c1.x >> 16) +
-              a1[2] * (double)(c1.y & 0xffffu) + a1[3] * (double)(c1.y >> 16);
-      }
-      if (q2 < n4) {
-        const double* a2 = Ak + 4 * q2;
-        s2 += a2[0] * (double)(c2.x & 0xffffu) + a2[1] * (double)(c2.x >> 16) +
-              a2[2] * (double)(c2.y & 0xffffu) + a2[3] * (double)(c2.y >> 16);
-      }
-      if (q3 < n4) {
-        const double* a3 = Ak + 4 * q3;
-        s3 += a3[0] * (double)(c3.x & 0xffffu) + a3[1] * (double)(c3.x >> 16) +
-              a3[2] * (double)(c3.y & 0xffffu) + a3[3] * (double)(c3.y >> 16);
+// Counters are read 8 bytes at a time: C = 4 (uint16) or 8 (uint8) adjacent genes.
+template <class CT>
+struct CntVec {
+  static constexpr int C = 8 / (int)sizeof(CT);
+  static __device__ __forceinline__ void unpack(const uint2 v, double (&e)[C]) {
+    if constexpr (sizeof(CT) == 2) {
+      e[0] = small_uint_to_double(__byte_perm(v.x, 0u, 0x4410));
+      e[1] = small_uint_to_double(__byte_perm(v.x, 0u, 0x4432));
+      e[2] = small_uint_to_double(__byte_perm(v.y, 0u, 0x4410));
+      e[3] = small_uint_to_double(__byte_perm(v.y, 0u, 0x4432));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        e[q] = small_uint_to_double(__byte_perm(v.x, 0u, 0x4440 + q));
+        e[4 + q] = small_uint_to_double(__byte_perm(v.y, 0u, 0x4440 + q));
       }
     }
-    s += s1 + s2 + s3;
-  } else {
-    for (int i = lane; i < N; i += 32) s += Ak[i] * (double)row[i];
   }
-  s = warp_sum(s);
-  if (lane == 0) {
-    const double ul = s * inv_sample;
-    u[l] = ul;
-    ratio[l] = R[l] / ul;
+};
+
+// MODE 0: out[type][i] += Y_li * E[S_li]            (m_step.py:88-89)
+// MODE 1: out[type][i] += E[S_li] * R_l / u_l       (m_step.py:123-125), active types only
+// A thread owns C adjacent genes (one 64-bit load of counters per cell) and walks a
+// chunk of the type-sorted cells.  The per-cell metadata of the chunk (row index, weight
+// R_l/u_l or 0 for a skipped row, type) is staged in shared memory once per CTA, so the
+// inner loop is: broadcast LDS of (row, weight), one 8-byte load, C x (byte permute, DADD,
+// DFMA); kColDepth independent loads are in flight per thread.  MODE 1 finishes opt_u
+// from mle_u_kernel's partial sums while staging.  HBM: 1 or 2 B per cell x gene (MODE 0 adds the 4 B count).
+constexpr int kColDepth = 8;
+constexpr int kColChunkMax = 512;  // cells per CTA (shared-memory staging)
+
+template <class CT, int MODE>
+__global__ void __launch_bounds__(kColThreads)
+mle_colsum_kernel(const float* Y, const CT* cnt, const int* G, const int* order,
+                  const double* u_acc, const double* R, double* u, const int* active, long long L,
+                  int N, int chunk, double inv_sample, double* out) {
+  constexpr int C = CntVec<CT>::C;
+  __shared__ int row_s[kColChunkMax];
+  __shared__ int type_s[kColChunkMax];
+  __shared__ double w_s[kColChunkMax];
+  const long long c0 = (long long)blockIdx.y * chunk;
+  const int n = (int)(min(L, c0 + chunk) - c0);
+  for (int t = threadIdx.x; t < n; t += kColThreads) {
+    const int l = order[c0 + t];
+    const int ty = G[l];
+    const bool use = MODE == 0 || active[ty];
+    row_s[t] = l;
+    type_s[t] = ty;
+    double w = use ? inv_sample : 0.0;
+    if (MODE == 1 && use) {  // opt_u (:108-115): u_l, and the weight R_l / u_l of the row
+      const double ul = u_acc[l] * inv_sample;
+      if (blockIdx.x == 0) u[l] = ul;
+      w = (R[l] / ul) * inv_sample;
+    }
+    w_s[t] = w;
+  }
+  __syncthreads();
+  const int i = C * (blockIdx.x * kColThreads + threadIdx.x);
+  if (i >= N) return;
+  const bool vec = (i + C - 1 < N) && ((N % C) == 0);  // 64-bit loads need 8-byte aligned rows
+  double acc[C];
+#pragma unroll
+  for (int q = 0; q < C; ++q) acc[q] = 0.0;
+  int cur = n > 0 ? type_s[0] : -1;
+  auto flush = [&](int next) {
+#pragma unroll
+    for (int q = 0; q < C; ++q) {
+      if (acc[q] != 0.0 && i + q < N) atomicAdd(&out[(size_t)cur * N + i + q], acc[q]);
+      acc[q] = 0.0;
+    }
+    cur = next;
+  };
+  auto loadv = [&](int l) {
+    const CT* row = cnt + (size_t)l * N + i;
+    if (vec) return *reinterpret_cast<const uint2*>(row);
+    unsigned long long bits = 0ull;  // ragged tail: assemble the same 8 bytes from scalars
+#pragma unroll
+    for (int q = 0; q < C; ++q)
+      if (i + q < N) bits |= (unsigned long long)row[q] << (8 * (int)sizeof(CT) * q);
+    return make_uint2((unsigned int)bits, (unsigned int)(bits >> 32));
+  };
+  for (int t0 = 0; t0 < n; t0 += kColDepth) {
+    uint2 v[kColDepth];
+#pragma unroll
+    for (int q = 0; q < kColDepth; ++q) {
+      const int t = t0 + q;
+      v[q] = (t < n && w_s[t] != 0.0) ? loadv(row_s[t]) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int q = 0; q < kColDepth; ++q) {
+      const int t = t0 + q;
+      if (t >= n) break;
+      if (type_s[t] != cur) flush(type_s[t]);
+      const double w = w_s[t];
+      if (w == 0.0) continue;
+      double e[C];
+      CntVec<CT>::unpack(v[q], e);
+      if (MODE == 0) {
+        const float* y = Y + (size_t)row_s[t] * N + i;
+#pragma unroll
+        for (int r = 0; r < C; ++r)
+          if (i + r < N) acc[r] = fma((double)y[r] * e[r], w, acc[r]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < C; ++r) acc[r] = fma(e[r], w, acc[r]);
+      }
+    }
+  }
+  flush(-1);
+}
+
+// u_l = sum_i A[i, G_l] E[S_li] and ratio_l = R_l / u_l for the cells of active types.
+// A warp takes kURows consecutive cells of the TYPE-SORTED order, so they share one column
+// of A (which stays in L1 for the CTA's other warps: same column).  A lane owns four
+// adjacent genes per step: one 4- or 8-byte load of counters per cell and two 16-byte
+// loads of A per kURows cells; kUDepth steps are in flight.  Counter -> double is a byte
+// permute and one DADD (small_uint_to_double).  The partial dot products of the gene
+// segments are summed into u_acc (zeroed by the caller); mle_colsum_kernel<., 1> turns them
+// into u_l and the weights R_l / u_l when it stages its cells.
+constexpr int kURows = 4, kUDepth = 2;
+
+template <class CT>
+__device__ __forceinline__ void load4(const CT* p, unsigned int (&c)[4]) {
+  if constexpr (sizeof(CT) == 1) {
+    const unsigned int v = *reinterpret_cast<const unsigned int*>(p);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) c[r] = __byte_perm(v, 0u, 0x4440 + r);
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    c[0] = __byte_perm(v.x, 0u, 0x4410);
+    c[1] = __byte_perm(v.x, 0u, 0x4432);
+    c[2] = __byte_perm(v.y, 0u, 0x4410);
+    c[3] = __byte_perm(v.y, 0u, 0x4432);
+  }
+}
+
+template <class CT>
+__global__ void __launch_bounds__(128)
+mle_u_kernel(const CT* cnt, const int* G, const int* order, const double* A, const int* active,
+             long long L, int N, int nseg, double* u_acc) {
+  const long long c0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kURows;
+  const int lane = threadIdx.x & 31, seg = blockIdx.y;
+  if (c0 >= L) return;
+  int l[kURows], ty[kURows];
+  bool same = true, any = false;
+  int ty0 = -1;
+#pragma unroll
+  for (int q = 0; q < kURows; ++q) {
+    l[q] = c0 + q < L ? order[c0 + q] : -1;
+    ty[q] = l[q] >= 0 ? G[l[q]] : -1;
+    if (ty[q] >= 0 && !active[ty[q]]) ty[q] = -1;
+    if (ty[q] >= 0) {
+      if (ty0 < 0) ty0 = ty[q];
+      same = same && ty[q] == ty0;
+      any = true;
+    }
+  }
+  if (!any) return;
+  double s[kURows];
+#pragma unroll
+  for (int q = 0; q < kURows; ++q) s[q] = 0.0;
+  if (same && (N & 3) == 0) {
+    const double2* Ak2 = reinterpret_cast<const double2*>(A + (size_t)ty0 * N);
+    const CT* row[kURows];
+#pragma unroll
+    for (int q = 0; q < kURows; ++q) row[q] = cnt + (size_t)(ty[q] >= 0 ? l[q] : l[0] >= 0 ? l[0] : 0) * N;
+    // this warp's segment of the gene axis (grid.y segments give short rows enough warps)
+    const int nv_all = N >> 2, per = (nv_all + nseg - 1) / nseg;
+    const int v_lo = seg * per, nv = min(nv_all, v_lo + per);
+    for (int v0 = v_lo + lane; v0 < nv; v0 += 32 * kUDepth) {
+      double2 a01[kUDepth], a23[kUDepth];
+      unsigned int c[kUDepth][kURows][4];
+#pragma unroll
+      for (int t = 0; t < kUDepth; ++t) {
+        const int v = min(v0 + 32 * t, nv - 1);  // clamped: out-of-range steps are weighted 0
+        a01[t] = Ak2[2 * v];
+        a23[t] = Ak2[2 * v + 1];
+#pragma unroll
+        for (int q = 0; q < kURows; ++q) load4<CT>(row[q] + 4 * (size_t)v, c[t][q]);
+      }
+#pragma unroll
+      for (int t = 0; t < kUDepth; ++t) {
+        if (v0 + 32 * t >= nv) break;
+#pragma unroll
+        for (int q = 0; q < kURows; ++q) {
+          s[q] = fma(a01[t].x, small_uint_to_double(c[t][q][0]), s[q]);
+          s[q] = fma(a01[t].y, small_uint_to_double(c[t][q][1]), s[q]);
+          s[q] = fma(a23[t].x, small_uint_to_double(c[t][q][2]), s[q]);
+          s[q] = fma(a23[t].y, small_uint_to_double(c[t][q][3]), s[q]);
+        }
+      }
+    }
+  } else {  // a type boundary inside the group, or ragged rows: one cell at a time
+    if (seg != 0) return;
+#pragma unroll
+    for (int q = 0; q < kURows; ++q) {
+      if (ty[q] < 0) continue;
+      const double* Ak = A + (size_t)ty[q] * N;
+      const CT* row = cnt + (size_t)l[q] * N;
+      double acc = 0.0;
+      for (int i = lane; i < N; i += 32) acc = fma(Ak[i], small_uint_to_double((unsigned int)row[i]), acc);
+      s[q] = acc;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kURows; ++q) {
+    const double tot = warp_sum(s[q]);
+    if (lane == 0 && ty[q] >= 0) atomicAdd(&u_acc[l[q]], tot);
   }
 }
 
@@ -254,6 +324,7 @@ struct StepArgs {
   const int* base;     // [K] halvings already rejected in earlier batches
   int N;
   double min_A, init_step;
+  int y_smem;          // trial column lives in dynamic shared memory (N doubles)
 };
 
 __device__ __forceinline__ void block_sum6(double* v, double* red) {
@@ -279,10 +350,13 @@ __device__ __forceinline__ void block_sum6(double* v, double* red) {
 //   projection = simplex_proj (utils.py:8-31) via proj_lambda.
 __global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
   __shared__ double red[6 * 32];
+  extern __shared__ double cand_ysm[];
   const int k = blockIdx.y, c = blockIdx.x, N = a.N, tid = threadIdx.x, T = blockDim.x;
   if (!a.act[k]) return;
   const double* Ak = a.A + (size_t)k * N;
-  double* y = a.cand + ((size_t)k * kCand + c) * N;
+  double* yout = a.cand + ((size_t)k * kCand + c) * N;
+  // the trial column is re-read by every pass of the projection: keep it on chip
+  double* y = a.y_smem ? cand_ysm : yout;
   const double* ci = a.cAinv + (size_t)k * N;
   const double* ca = a.cA + (size_t)k * N;
   const double* c0 = a.coeffA + (size_t)k * N;
@@ -308,7 +382,7 @@ __global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
     const double g = -((ci[i] / x + ca[i] * x + cc) * invN);
     const double nv = fmax(y[i] + lam, a.min_A);
     const double Gt = (x - nv) / step;
-    y[i] = nv;
+    yout[i] = nv;
     v[0] += ci[i] * log(nv);
     v[1] += ca[i] * nv * nv;
     v[2] += cc * nv;
@@ -333,7 +407,7 @@ __global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
 // win[k] = index of the accepted trial, -1 if none.
 __global__ void mle_decide_kernel(const double* cres, const int* act, int* act_next, int* niter,
                                   int* base, int* halv, double* delta, int* win, int K,
-                                  double conv, int maxiter) {
+                                  double conv, int maxiter, int ncand) {
   const int k = threadIdx.x;
   if (k >= K) return;
   win[k] = -1;
@@ -342,14 +416,14 @@ __global__ void mle_decide_kernel(const double* cres, const int* act, int* act_n
     return;
   }
   int w = -1;
-  for (int c = 0; c < kCand; ++c)
+  for (int c = 0; c < ncand; ++c)
     if (cres[((size_t)k * kCand + c) * 4] != 0.0) {
       w = c;
       break;
     }
-  if (w < 0 && base[k] + kCand >= 1024) w = kCand - 1;  // step underflow guard
+  if (w < 0 && base[k] + ncand >= 1024) w = ncand - 1;  // step underflow guard
   if (w < 0) {  // every trial of this batch was rejected: keep halving
-    base[k] += kCand;
+    base[k] += ncand;
     act_next[k] = 1;
     return;
   }
@@ -441,6 +515,8 @@ static void transpose_NK_to_KN(const double* h, std::vector<double>& t, int N, i
 static int colsum_chunk(const Mle* m, long long L, int gx, int* ny_out) {
   long long want = std::max<long long>(1, (8LL * m->num_sms + gx - 1) / gx);
   long long ny = std::min<long long>(std::min<long long>(L, want), 65535);
+  ny = std::max<long long>(ny, (L + kColChunkMax - 1) / kColChunkMax);  // smem staging per CTA
+  URSM_REQUIRE(ny <= 65535, "M-step: too many cells in one shard for the column-sum grid");
   int chunk = (int)((L + ny - 1) / ny);
   *ny_out = (int)((L + chunk - 1) / chunk);
   return chunk;
@@ -533,12 +609,19 @@ int ursm_mle_begin(ursm_mle* mm, double* d_part, void* stream) {
   URSM_CUDA(cudaMemsetAsync(d_part, 0, (size_t)m->K * m->N * sizeof(double), st));
   if (m->sc) {
     ScShard* s = m->sc;
-    const int gx = (m->N + kColGenes * kColThreads - 1) / (kColGenes * kColThreads);
+    URSM_REQUIRE(s->cnt_w > 0, "ursm_mle_begin: the single-cell E-step has not run yet");
+    const int C = 8 / s->cnt_w;
+    const int gx = (m->N + C * kColThreads - 1) / (C * kColThreads);
     int ny;
     const int chunk = colsum_chunk(m, s->L, gx, &ny);
-    mle_colsum_kernel<0><<<dim3(gx, ny), kColThreads, 0, st>>>(
-        s->Y, s->cnt.p, s->G.p, s->order.p, nullptr, nullptr, s->L, m->N, chunk,
-        1.0 / s->sample, d_part);
+    if (s->cnt_w == 1)
+      mle_colsum_kernel<unsigned char, 0><<<dim3(gx, ny), kColThreads, 0, st>>>(
+          s->Y, s->cnt.p, s->G.p, s->order.p, nullptr, nullptr, nullptr, nullptr, s->L, m->N,
+          chunk, 1.0 / s->sample, d_part);
+    else
+      mle_colsum_kernel<unsigned short, 0><<<dim3(gx, ny), kColThreads, 0, st>>>(
+          s->Y, reinterpret_cast<const unsigned short*>(s->cnt.p), s->G.p, s->order.p, nullptr,
+          nullptr, nullptr, nullptr, s->L, m->N, chunk, 1.0 / s->sample, d_part);
     URSM_LAUNCH_CHECK();
   }
   URSM_API_END
@@ -550,17 +633,35 @@ static void mle_pass(Mle* m, double* d_part, cudaStream_t st) {
   const size_t KN = (size_t)m->K * m->N;
   URSM_CUDA(cudaMemsetAsync(d_part, 0, (KN + m->K) * sizeof(double), st));
   const double inv = 1.0 / s->sample;
-  mle_u_kernel<<<(unsigned)((s->L + 7) / 8), 256, 0, st>>>(s->cnt.p, s->G.p, m->A.p, s->R.p,
-                                                           m->act_cur.p, s->L, m->N, inv, m->u.p,
-                                                           m->ratio.p);
-  URSM_LAUNCH_CHECK();
-  const int gx = (m->N + kColGenes * kColThreads - 1) / (kColGenes * kColThreads);
+  URSM_REQUIRE(s->cnt_w > 0, "M-step: the single-cell E-step has not run yet");
+  const int C = 8 / s->cnt_w;
+  const int gx = (m->N + C * kColThreads - 1) / (C * kColThreads);
   int ny;
   const int chunk = colsum_chunk(m, s->L, gx, &ny);
-  mle_colsum_kernel<1><<<dim3(gx, ny), kColThreads, 0, st>>>(s->Y, s->cnt.p, s->G.p, s->order.p,
-                                                            m->ratio.p, m->act_cur.p, s->L, m->N,
-                                                            chunk, inv, d_part);
-  URSM_LAUNCH_CHECK();
+  const unsigned ub = (unsigned)((s->L + 4 * kURows - 1) / (4 * kURows));
+  // enough warps to cover the HBM latency: split the gene axis when there are few cells
+  const long long warps = (s->L + kURows - 1) / kURows;
+  int nseg = (int)std::max<long long>(1, (48LL * m->num_sms + warps - 1) / warps);
+  nseg = std::max(1, std::min(nseg, (m->N / 4 + 63) / 64));
+  m->ratio.zero(st);  // u_acc: partial dot products
+  if (s->cnt_w == 1) {
+    mle_u_kernel<unsigned char><<<dim3(ub, nseg), 128, 0, st>>>(
+        s->cnt.p, s->G.p, s->order.p, m->A.p, m->act_cur.p, s->L, m->N, nseg, m->ratio.p);
+    URSM_LAUNCH_CHECK();
+    mle_colsum_kernel<unsigned char, 1><<<dim3(gx, ny), kColThreads, 0, st>>>(
+        s->Y, s->cnt.p, s->G.p, s->order.p, m->ratio.p, s->R.p, m->u.p, m->act_cur.p, s->L, m->N,
+        chunk, inv, d_part);
+    URSM_LAUNCH_CHECK();
+  } else {
+    const unsigned short* c16 = reinterpret_cast<const unsigned short*>(s->cnt.p);
+    mle_u_kernel<unsigned short><<<dim3(ub, nseg), 128, 0, st>>>(
+        c16, s->G.p, s->order.p, m->A.p, m->act_cur.p, s->L, m->N, nseg, m->ratio.p);
+    URSM_LAUNCH_CHECK();
+    mle_colsum_kernel<unsigned short, 1><<<dim3(gx, ny), kColThreads, 0, st>>>(
+        s->Y, c16, s->G.p, s->order.p, m->ratio.p, s->R.p, m->u.p, m->act_cur.p, s->L, m->N, chunk,
+        inv, d_part);
+    URSM_LAUNCH_CHECK();
+  }
   mle_rlogu_kernel<<<(unsigned)((s->L + 255) / 256), 256, 0, st>>>(s->G.p, s->R.p, m->u.p, s->L,
                                                                   d_part + KN);
   URSM_LAUNCH_CHECK();
@@ -624,12 +725,24 @@ int ursm_mle_opt_step(ursm_mle* mm, const double* d_cconst_part, void* stream) {
   a.N = m->N;
   a.min_A = m->min_A;
   a.init_step = m->init_step;
+  // a batch is ncand <= kCand trial steps per column, sized so that all ncand x K CTAs are
+  // resident in one wave (the accepted step does not depend on the batch size)
+  const int ncand = std::max(1, std::min(kCand, m->num_sms / m->K));
   const int T = std::max(64, std::min(1024, (m->N / 4 + 31) / 32 * 32));
-  mle_cand_kernel<<<dim3(kCand, m->K), T, 0, st>>>(a);
+  const size_t ybytes = (size_t)m->N * sizeof(double);
+  a.y_smem = ybytes <= (size_t)160 * 1024 ? 1 : 0;
+  const size_t dyn = a.y_smem ? ybytes : 0;
+  static size_t configured = 0;
+  if (dyn > 48 * 1024 && dyn > configured) {
+    URSM_CUDA(cudaFuncSetAttribute(mle_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)dyn));
+    configured = dyn;
+  }
+  mle_cand_kernel<<<dim3(ncand, m->K), T, dyn, st>>>(a);
   URSM_LAUNCH_CHECK();
   mle_decide_kernel<<<1, 32, 0, st>>>(m->cres.p, m->act_cur.p, m->act_next.p, m->niter.p,
                                       m->base.p, m->halv.p, m->delta.p, m->win.p, m->K, m->conv,
-                                      m->maxiter);
+                                      m->maxiter, ncand);
   URSM_LAUNCH_CHECK();
   mle_copy_kernel<<<dim3(m->K, 8), 256, 0, st>>>(m->A.p, m->cand.p, m->win.p, m->N);
   URSM_LAUNCH_CHECK();

@@ -55,7 +55,8 @@ struct ScGibbsArgs {
   int sweep0;           // first sweep index (debug: run sweep `sweep0` only)
   unsigned long long key;
   PhiloxKeys rk;        // round keys of `key` (constant-bank operands of the Philox rounds)
-  unsigned short* cnt;  // [L][N]
+  void* cnt;            // [L][N] counters, cnt_w bytes each
+  int cnt_w;
   double* cellmom;      // [4][L]
   double* stats;        // coeffA[K][N] | coeffAsq[K][N] | elbo | sk | skk | st | stt
   float* scratch;       // [grid][slots][2]
@@ -420,7 +421,10 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
     __syncthreads();
     for (int i = tid; i < N; i += T) {
       const int slot = slot_of_gene(i, g, T, inv_g);
-      a.cnt[(size_t)l * N + i] = cnt_s[slot];
+      if (a.cnt_w == 1)
+        static_cast<unsigned char*>(a.cnt)[(size_t)l * N + i] = (unsigned char)cnt_s[slot];
+      else
+        static_cast<unsigned short*>(a.cnt)[(size_t)l * N + i] = cnt_s[slot];
       if (a.w_out) a.w_out[(size_t)l * N + i] = w_s[slot];
       if (a.S_out) {
         const int to = slot % T, j = slot / T;
@@ -499,7 +503,8 @@ __global__ void cast_f64_f32_kernel(const double* in, float* out, size_t n) {
   for (; i < n; i += stride) out[i] = (float)in[i];
 }
 
-__global__ void cnt_to_f64_kernel(const unsigned short* cnt, double* out, size_t n, double inv) {
+template <class CT>
+__global__ void cnt_to_f64_kernel(const CT* cnt, double* out, size_t n, double inv) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = (double)cnt[i] * inv;
@@ -590,8 +595,6 @@ static void sc_finish_create(ScShard* s, const int64_t* h_G) {
   s->R.alloc(L);
   sc_rowsum_kernel<<<(unsigned)L, 256>>>(s->Y, L, s->N, s->R.p);
   URSM_LAUNCH_CHECK();
-  s->cnt.alloc((size_t)L * s->N);
-  s->cnt.zero();
   s->cellmom.alloc(4 * (size_t)L);
   s->cellmom.zero();
   s->counter.alloc(1);
@@ -619,6 +622,7 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
   a.mu_t = s->ptau[0];
   a.prec_t = 1.0 / s->ptau[1];
   a.cnt = s->cnt.p;
+  a.cnt_w = s->cnt_w;
   a.cellmom = s->cellmom.p;
   a.scratch = s->scratch.p;
   a.flush_every = 16;
@@ -768,6 +772,7 @@ int ursm_sc_gibbs(ursm_sc* sc, int32_t burnin, int32_t sample, int32_t thin, uin
   a.rk = philox_keys(a.key);
   a.stats = d_stats;
   s->sample = sample;
+  s->cnt_ensure((sample <= 255 && !getenv("URSM_SC_CNT16")) ? 1 : 2);
   sc_launch(s, a, st);
   URSM_API_END
 }
@@ -791,14 +796,19 @@ int ursm_sc_get_exp_S(ursm_sc* sc, double* h_out, int64_t row0, int64_t nrows) {
   URSM_API_BEGIN
   ScShard* s = reinterpret_cast<ScShard*>(sc);
   URSM_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= s->L, "ursm_sc_get_exp_S: bad rows");
+  URSM_REQUIRE(s->cnt_w > 0, "ursm_sc_get_exp_S: no E-step has run yet");
   const size_t rows_per = std::max<size_t>(1, ((size_t)1 << 24) / s->N);
   DevBuf<double> stage;
   stage.alloc(std::min<size_t>(rows_per, (size_t)nrows) * s->N);
   URSM_CUDA(cudaDeviceSynchronize());
   for (int64_t r = 0; r < nrows; r += rows_per) {
     size_t m = std::min<size_t>(rows_per, (size_t)(nrows - r)) * s->N;
-    cnt_to_f64_kernel<<<1184, 256>>>(s->cnt.p + (size_t)(row0 + r) * s->N, stage.p, m,
-                                     1.0 / s->sample);
+    const size_t first = (size_t)(row0 + r) * s->N;
+    if (s->cnt_w == 1)
+      cnt_to_f64_kernel<<<1184, 256>>>(s->cnt.p + first, stage.p, m, 1.0 / s->sample);
+    else
+      cnt_to_f64_kernel<<<1184, 256>>>(reinterpret_cast<const unsigned short*>(s->cnt.p) + first,
+                                       stage.p, m, 1.0 / s->sample);
     URSM_LAUNCH_CHECK();
     URSM_CUDA(cudaMemcpy(h_out + (size_t)r * s->N, stage.p, m * sizeof(double),
                          cudaMemcpyDeviceToHost));
@@ -815,7 +825,9 @@ int ursm_sc_inject(ursm_sc* sc, const double* h_w, const int64_t* h_S, const dou
                "ursm_sc_inject: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t LN = (size_t)s->L * s->N;
-  if (reset) {
+  if (reset || s->cnt_w != 2) {
+    URSM_REQUIRE(reset, "ursm_sc_inject: accumulate onto a Gibbs run is not supported; reset first");
+    s->cnt_ensure(2);  // the parity hook always counts in 16 bits
     URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_sc_stats_len(sc) * sizeof(double), st));
     s->cnt.zero(st);
     s->cellmom.zero(st);
@@ -833,7 +845,8 @@ int ursm_sc_inject(ursm_sc* sc, const double* h_w, const int64_t* h_S, const dou
   URSM_CUDA(cudaMemcpyAsync(kt.p, h_kappa, s->L * sizeof(double), cudaMemcpyHostToDevice, st));
   URSM_CUDA(cudaMemcpyAsync(kt.p + s->L, h_tau, s->L * sizeof(double), cudaMemcpyHostToDevice, st));
   sc_inject_kernel<<<(unsigned)s->L, 256, 0, st>>>(w.p, S.p, kt.p, kt.p + s->L, s->G.p, s->L, s->N,
-                                                   s->K, 1.0 / sample, s->cnt.p, s->cellmom.p,
+                                                   s->K, 1.0 / sample,
+                                                   reinterpret_cast<unsigned short*>(s->cnt.p), s->cellmom.p,
                                                    d_stats);
   URSM_LAUNCH_CHECK();
   URSM_CUDA(cudaStreamSynchronize(st));
@@ -883,6 +896,7 @@ int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kapp
   a.kt_out = ktout.p;
   a.rounds_out = rounds.p;
   s->sample = 1;
+  s->cnt_ensure(2);
   sc_launch(s, a, 0);
   URSM_CUDA(cudaDeviceSynchronize());
   if (h_w_out) URSM_CUDA(cudaMemcpy(h_w_out, wout.p, LN * sizeof(float), cudaMemcpyDeviceToHost));

@@ -14,7 +14,17 @@ struct ScShard {
   const float* Y = nullptr;      // [L][N] counts (owned or borrowed)
   DevBuf<int> G, order;          // types; local cell ids sorted by type
   DevBuf<double> R;              // read depth per cell
-  DevBuf<unsigned short> cnt;    // [L][N] number of retained sweeps with S = 1
+  // [L][N] number of retained sweeps with S = 1 (E[S] = cnt / sample, exact).  One byte
+  // per entry when sample <= 255, two otherwise: the M-step streams this matrix twice per
+  // outer iteration, so its width is the M-step's HBM traffic.
+  DevBuf<unsigned char> cnt;
+  int cnt_w = 0;                 // bytes per counter (0: not allocated yet)
+  void cnt_ensure(int width) {
+    if (cnt_w == width) return;
+    cnt.alloc((size_t)L * N * width);
+    cnt.zero();
+    cnt_w = width;
+  }
   DevBuf<double> cellmom;        // [4][L] E kappa, E tau, E kappa^2, E tau^2
   DevBuf<int> counter;           // work counter of the persistent kernel
   DevBuf<double> A;              // [N][K] fp64 parameters (row-major, as given)
