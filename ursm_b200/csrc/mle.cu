@@ -31,7 +31,8 @@ struct Mle {
   const double* coeffA = nullptr;
   DevBuf<double> u, ratio;               // [L] u_l; partial sums of the u pass (u_acc)
   DevBuf<int> act_cur, act_next;         // [K] columns in opt_Ak at the start / end of an iteration
-  DevBuf<int> niter, base, halv, win;    // [K] outer iterations, halvings already tried, total halvings
+  DevBuf<int> type_start;                // [K+1] offsets of the types in the sorted cell order
+  DevBuf<int> niter, base, halv;         // [K] outer iterations, halvings already tried, total halvings
   DevBuf<double> cand;                   // [K][kCand][N] candidate columns of one backtracking batch
   DevBuf<double> cres;                   // [K][kCand][4]: accepted?, objective, ||dA||_1, step
   DevBuf<double> delta;                  // [K] last accepted ||dA_k||_1
@@ -162,15 +163,19 @@ mle_colsum_kernel(const float* Y, const CT* cnt, const int* G, const int* order,
   flush(-1);
 }
 
-// u_l = sum_i A[i, G_l] E[S_li] and ratio_l = R_l / u_l for the cells of active types.
-// A warp takes kURows consecutive cells of the TYPE-SORTED order, so they share one column
-// of A (which stays in L1 for the CTA's other warps: same column).  A lane owns four
-// adjacent genes per step: one 4- or 8-byte load of counters per cell and two 16-byte
-// loads of A per kURows cells; kUDepth steps are in flight.  Counter -> double is a byte
-// permute and one DADD (small_uint_to_double).  The partial dot products of the gene
-// segments are summed into u_acc (zeroed by the caller); mle_colsum_kernel<., 1> turns them
-// into u_l and the weights R_l / u_l when it stages its cells.
-constexpr int kURows = 4, kUDepth = 2;
+// u_l = sum_i A[i, G_l] E[S_li] for the cells of active types (opt_u, :108-115), as
+// partial dot products summed into u_acc (zeroed by the caller); mle_colsum_kernel<., 1>
+// turns them into u_l and the weights R_l / u_l when it stages its cells.
+// A CTA owns a block of consecutive cells of the TYPE-SORTED order and one segment of the
+// gene axis.  For every run of same-type cells in its block it stages that type's segment
+// of A in shared memory once (split into the (a0,a1) and (a2,a3) halves of each group of
+// four genes, so that the 16-byte reads are conflict free) and its warps then stream the
+// counters: a warp takes kURows cells at a time, a lane owns four adjacent genes per step
+// (one 4- or 8-byte counter load per cell), kUDepth steps in flight.  A is read from L2
+// once per CTA and run instead of once per cell; counter -> double is a byte permute and
+// one DADD (small_uint_to_double).
+constexpr int kURows = 4, kUDepth = 2, kUThreads = 256;
+constexpr int kUSegGenes = 4096;  // genes per segment: 32 KB of A in shared memory
 
 template <class CT>
 __device__ __forceinline__ void load4(const CT* p, unsigned int (&c)[4]) {
@@ -188,77 +193,81 @@ __device__ __forceinline__ void load4(const CT* p, unsigned int (&c)[4]) {
 }
 
 template <class CT>
-__global__ void __launch_bounds__(128)
-mle_u_kernel(const CT* cnt, const int* G, const int* order, const double* A, const int* active,
-             long long L, int N, int nseg, double* u_acc) {
-  const long long c0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kURows;
-  const int lane = threadIdx.x & 31, seg = blockIdx.y;
-  if (c0 >= L) return;
-  int l[kURows], ty[kURows];
-  bool same = true, any = false;
-  int ty0 = -1;
-#pragma unroll
-  for (int q = 0; q < kURows; ++q) {
-    l[q] = c0 + q < L ? order[c0 + q] : -1;
-    ty[q] = l[q] >= 0 ? G[l[q]] : -1;
-    if (ty[q] >= 0 && !active[ty[q]]) ty[q] = -1;
-    if (ty[q] >= 0) {
-      if (ty0 < 0) ty0 = ty[q];
-      same = same && ty[q] == ty0;
-      any = true;
-    }
-  }
-  if (!any) return;
-  double s[kURows];
-#pragma unroll
-  for (int q = 0; q < kURows; ++q) s[q] = 0.0;
-  if (same && (N & 3) == 0) {
-    const double2* Ak2 = reinterpret_cast<const double2*>(A + (size_t)ty0 * N);
-    const CT* row[kURows];
-#pragma unroll
-    for (int q = 0; q < kURows; ++q) row[q] = cnt + (size_t)(ty[q] >= 0 ? l[q] : l[0] >= 0 ? l[0] : 0) * N;
-    // this warp's segment of the gene axis (grid.y segments give short rows enough warps)
-    const int nv_all = N >> 2, per = (nv_all + nseg - 1) / nseg;
-    const int v_lo = seg * per, nv = min(nv_all, v_lo + per);
-    for (int v0 = v_lo + lane; v0 < nv; v0 += 32 * kUDepth) {
-      double2 a01[kUDepth], a23[kUDepth];
-      unsigned int c[kUDepth][kURows][4];
-#pragma unroll
-      for (int t = 0; t < kUDepth; ++t) {
-        const int v = min(v0 + 32 * t, nv - 1);  // clamped: out-of-range steps are weighted 0
-        a01[t] = Ak2[2 * v];
-        a23[t] = Ak2[2 * v + 1];
-#pragma unroll
-        for (int q = 0; q < kURows; ++q) load4<CT>(row[q] + 4 * (size_t)v, c[t][q]);
+__global__ void __launch_bounds__(kUThreads)
+mle_u_kernel(const CT* cnt, const int* order, const int* type_start, const double* A,
+             const int* active, long long L, int N, int K, int rows_per_cta, int seg_genes,
+             double* u_acc) {
+  __shared__ double2 A01[kUSegGenes / 4], A23[kUSegGenes / 4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kUThreads >> 5;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(L, r0 + rows_per_cta);
+  const int g_lo = blockIdx.y * seg_genes, g_hi = min(N, g_lo + seg_genes);
+  const bool vec = (N & 3) == 0;  // rows keep the alignment of the vector loads
+  const int nv = (g_hi - g_lo) >> 2;  // groups of four genes in this segment (vec only)
+  for (int k = 0; k < K; ++k) {
+    const long long lo = max(r0, (long long)type_start[k]);
+    const long long hi = min(r1, (long long)type_start[k + 1]);
+    if (lo >= hi || !active[k]) continue;
+    const double* Ak = A + (size_t)k * N;
+    if (vec) {
+      __syncthreads();  // previous run's readers are done
+      const double2* src = reinterpret_cast<const double2*>(Ak + g_lo);
+      for (int v = tid; v < nv; v += kUThreads) {
+        A01[v] = src[2 * v];
+        A23[v] = src[2 * v + 1];
       }
+      __syncthreads();
+    }
+    for (long long c0 = lo + (long long)warp * kURows; c0 < hi; c0 += (long long)nwarp * kURows) {
+      int l[kURows];
+      double s[kURows];
 #pragma unroll
-      for (int t = 0; t < kUDepth; ++t) {
-        if (v0 + 32 * t >= nv) break;
+      for (int q = 0; q < kURows; ++q) {
+        l[q] = c0 + q < hi ? order[c0 + q] : -1;
+        s[q] = 0.0;
+      }
+      if (vec) {
+        const CT* row[kURows];
+#pragma unroll
+        for (int q = 0; q < kURows; ++q) row[q] = cnt + (size_t)(l[q] >= 0 ? l[q] : l[0]) * N + g_lo;
+        for (int v0 = lane; v0 < nv; v0 += 32 * kUDepth) {
+          unsigned int c[kUDepth][kURows][4];
+#pragma unroll
+          for (int t = 0; t < kUDepth; ++t) {
+            const int v = min(v0 + 32 * t, nv - 1);  // clamped; out-of-range steps are skipped
+#pragma unroll
+            for (int q = 0; q < kURows; ++q) load4<CT>(row[q] + 4 * (size_t)v, c[t][q]);
+          }
+#pragma unroll
+          for (int t = 0; t < kUDepth; ++t) {
+            const int v = v0 + 32 * t;
+            if (v >= nv) break;
+            const double2 a01 = A01[v], a23 = A23[v];
+#pragma unroll
+            for (int q = 0; q < kURows; ++q) {
+              s[q] = fma(a01.x, small_uint_to_double(c[t][q][0]), s[q]);
+              s[q] = fma(a01.y, small_uint_to_double(c[t][q][1]), s[q]);
+              s[q] = fma(a23.x, small_uint_to_double(c[t][q][2]), s[q]);
+              s[q] = fma(a23.y, small_uint_to_double(c[t][q][3]), s[q]);
+            }
+          }
+        }
+      } else {  // ragged rows: scalar loads
 #pragma unroll
         for (int q = 0; q < kURows; ++q) {
-          s[q] = fma(a01[t].x, small_uint_to_double(c[t][q][0]), s[q]);
-          s[q] = fma(a01[t].y, small_uint_to_double(c[t][q][1]), s[q]);
-          s[q] = fma(a23[t].x, small_uint_to_double(c[t][q][2]), s[q]);
-          s[q] = fma(a23[t].y, small_uint_to_double(c[t][q][3]), s[q]);
+          if (l[q] < 0) continue;
+          const CT* row = cnt + (size_t)l[q] * N;
+          double acc = 0.0;
+          for (int i = g_lo + lane; i < g_hi; i += 32)
+            acc = fma(Ak[i], small_uint_to_double((unsigned int)row[i]), acc);
+          s[q] = acc;
         }
       }
-    }
-  } else {  // a type boundary inside the group, or ragged rows: one cell at a time
-    if (seg != 0) return;
 #pragma unroll
-    for (int q = 0; q < kURows; ++q) {
-      if (ty[q] < 0) continue;
-      const double* Ak = A + (size_t)ty[q] * N;
-      const CT* row = cnt + (size_t)l[q] * N;
-      double acc = 0.0;
-      for (int i = lane; i < N; i += 32) acc = fma(Ak[i], small_uint_to_double((unsigned int)row[i]), acc);
-      s[q] = acc;
+      for (int q = 0; q < kURows; ++q) {
+        const double tot = warp_sum(s[q]);
+        if (lane == 0 && l[q] >= 0) atomicAdd(&u_acc[l[q]], tot);
+      }
     }
-  }
-#pragma unroll
-  for (int q = 0; q < kURows; ++q) {
-    const double tot = warp_sum(s[q]);
-    if (lane == 0 && ty[q] >= 0) atomicAdd(&u_acc[l[q]], tot);
   }
 }
 
@@ -402,51 +411,50 @@ __global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
   }
 }
 
-// Per column (one thread each): accept the first passing trial of the batch (or
-// schedule the next batch of halvings) and advance the opt_Ak loop state (:164-181).
-// win[k] = index of the accepted trial, -1 if none.
-__global__ void mle_decide_kernel(const double* cres, const int* act, int* act_next, int* niter,
-                                  int* base, int* halv, double* delta, int* win, int K,
-                                  double conv, int maxiter, int ncand) {
-  const int k = threadIdx.x;
-  if (k >= K) return;
-  win[k] = -1;
+// One CTA per column: thread 0 accepts the first passing trial of the batch (or schedules
+// the next batch of halvings) and advances the opt_Ak loop state (:164-181); the CTA
+// then installs the accepted trial column, A[k] <- cand[k][w].
+__global__ void __launch_bounds__(1024)
+mle_decide_copy_kernel(const double* cres, const int* act, int* act_next, int* niter, int* base,
+                       int* halv, double* delta, double* A, const double* cand, int N,
+                       double conv, int maxiter, int ncand) {
+  __shared__ int win_s;
+  const int k = blockIdx.x;
   if (!act[k]) {
-    act_next[k] = 0;
+    if (threadIdx.x == 0) act_next[k] = 0;
     return;
   }
-  int w = -1;
-  for (int c = 0; c < ncand; ++c)
-    if (cres[((size_t)k * kCand + c) * 4] != 0.0) {
-      w = c;
-      break;
+  if (threadIdx.x == 0) {
+    int w = -1;
+    for (int c = 0; c < ncand; ++c)
+      if (cres[((size_t)k * kCand + c) * 4] != 0.0) {
+        w = c;
+        break;
+      }
+    if (w < 0 && base[k] + ncand >= 1024) w = ncand - 1;  // step underflow guard
+    if (w < 0) {  // every trial of this batch was rejected: keep halving
+      base[k] += ncand;
+      act_next[k] = 1;
+    } else {
+      const double d = cres[((size_t)k * kCand + w) * 4 + 2];
+      delta[k] = d;
+      halv[k] += base[k] + w;
+      base[k] = 0;
+      const int n = ++niter[k];
+      act_next[k] = (d > conv && n < maxiter) ? 1 : 0;
     }
-  if (w < 0 && base[k] + ncand >= 1024) w = ncand - 1;  // step underflow guard
-  if (w < 0) {  // every trial of this batch was rejected: keep halving
-    base[k] += ncand;
-    act_next[k] = 1;
-    return;
+    win_s = w;
   }
-  const double d = cres[((size_t)k * kCand + w) * 4 + 2];
-  win[k] = w;
-  delta[k] = d;
-  halv[k] += base[k] + w;
-  base[k] = 0;
-  const int n = ++niter[k];
-  act_next[k] = (d > conv && n < maxiter) ? 1 : 0;
-}
-
-// A[k] <- accepted trial column
-__global__ void mle_copy_kernel(double* A, const double* cand, const int* win, int N) {
-  const int k = blockIdx.x, w = win[k];
+  __syncthreads();
+  const int w = win_s;
   if (w < 0) return;
   const double* src = cand + ((size_t)k * kCand + w) * N;
-  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < N; i += gridDim.y * blockDim.x)
-    A[(size_t)k * N + i] = src[i];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) A[(size_t)k * N + i] = src[i];
 }
 
 // part[k][:] <- part_local[k][:] for the columns that were stepped; the per-type
-// sum_l R_l log u_l tail is refreshed for every type; then the loop state advances.
+// sum_l R_l log u_l tail is refreshed for every type.  (The loop state advances by the
+// host swapping the act_cur / act_next buffers: no kernel.)
 __global__ void mle_merge_kernel(const double* part_local, double* part, const int* act, int N,
                                  int K) {
   const int k = blockIdx.y;
@@ -458,10 +466,6 @@ __global__ void mle_merge_kernel(const double* part_local, double* part, const i
   if (!act[k]) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) part[(size_t)k * N + i] = part_local[(size_t)k * N + i];
-}
-
-__global__ void mle_advance_kernel(int* act_cur, const int* act_next, int K) {
-  if (threadIdx.x < K) act_cur[threadIdx.x] = act_next[threadIdx.x];
 }
 
 // A_k = simplex_proj(v / sum v)   (m_step.py:149-153, utils.py:8-31)
@@ -552,7 +556,6 @@ int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t
     m->niter.alloc(K);
     m->base.alloc(K);
     m->halv.alloc(K);
-    m->win.alloc(K);
     m->delta.alloc(K);
     m->act_cur.zero();
     m->act_next.zero();
@@ -560,6 +563,10 @@ int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t
     m->cres.alloc((size_t)K * kCand * 4);
     m->terms.alloc(4);
     if (m->sc) {
+      std::vector<int> ts(K + 1);
+      for (int k = 0; k <= K; ++k) ts[k] = (int)m->sc->type_start[k];
+      m->type_start.alloc(K + 1);
+      URSM_CUDA(cudaMemcpy(m->type_start.p, ts.data(), (K + 1) * sizeof(int), cudaMemcpyHostToDevice));
       m->u.alloc(m->sc->L);
       m->u.zero();
       m->ratio.alloc(m->sc->L);
@@ -638,15 +645,22 @@ static void mle_pass(Mle* m, double* d_part, cudaStream_t st) {
   const int gx = (m->N + C * kColThreads - 1) / (C * kColThreads);
   int ny;
   const int chunk = colsum_chunk(m, s->L, gx, &ny);
-  const unsigned ub = (unsigned)((s->L + 4 * kURows - 1) / (4 * kURows));
-  // enough warps to cover the HBM latency: split the gene axis when there are few cells
-  const long long warps = (s->L + kURows - 1) / kURows;
-  int nseg = (int)std::max<long long>(1, (48LL * m->num_sms + warps - 1) / warps);
-  nseg = std::max(1, std::min(nseg, (m->N / 4 + 63) / 64));
+  // u pass geometry: blocks of cells x gene segments (at most kUSegGenes genes, a multiple
+  // of the 128 genes a warp covers per step), sized for ~4 CTAs per SM over the whole grid
+  const int group = (kUThreads / 32) * kURows;
+  int nseg = (m->N + kUSegGenes - 1) / kUSegGenes;
+  long long rows = (s->L * nseg + 4LL * m->num_sms - 1) / (4LL * m->num_sms);
+  rows = std::max<long long>(group, std::min<long long>(8 * group, (rows + group - 1) / group * group));
+  const unsigned ub = (unsigned)((s->L + rows - 1) / rows);
+  if ((long long)ub * nseg < 4LL * m->num_sms)
+    nseg = (int)std::min<long long>((m->N + 127) / 128, (4LL * m->num_sms + ub - 1) / ub);
+  const int seg_genes = std::min(kUSegGenes, ((m->N + nseg - 1) / nseg + 127) / 128 * 128);
+  nseg = (m->N + seg_genes - 1) / seg_genes;
   m->ratio.zero(st);  // u_acc: partial dot products
   if (s->cnt_w == 1) {
-    mle_u_kernel<unsigned char><<<dim3(ub, nseg), 128, 0, st>>>(
-        s->cnt.p, s->G.p, s->order.p, m->A.p, m->act_cur.p, s->L, m->N, nseg, m->ratio.p);
+    mle_u_kernel<unsigned char><<<dim3(ub, nseg), kUThreads, 0, st>>>(
+        s->cnt.p, s->order.p, m->type_start.p, m->A.p, m->act_cur.p, s->L, m->N, m->K, (int)rows,
+        seg_genes, m->ratio.p);
     URSM_LAUNCH_CHECK();
     mle_colsum_kernel<unsigned char, 1><<<dim3(gx, ny), kColThreads, 0, st>>>(
         s->Y, s->cnt.p, s->G.p, s->order.p, m->ratio.p, s->R.p, m->u.p, m->act_cur.p, s->L, m->N,
@@ -654,8 +668,9 @@ static void mle_pass(Mle* m, double* d_part, cudaStream_t st) {
     URSM_LAUNCH_CHECK();
   } else {
     const unsigned short* c16 = reinterpret_cast<const unsigned short*>(s->cnt.p);
-    mle_u_kernel<unsigned short><<<dim3(ub, nseg), 128, 0, st>>>(
-        c16, s->G.p, s->order.p, m->A.p, m->act_cur.p, s->L, m->N, nseg, m->ratio.p);
+    mle_u_kernel<unsigned short><<<dim3(ub, nseg), kUThreads, 0, st>>>(
+        c16, s->order.p, m->type_start.p, m->A.p, m->act_cur.p, s->L, m->N, m->K, (int)rows,
+        seg_genes, m->ratio.p);
     URSM_LAUNCH_CHECK();
     mle_colsum_kernel<unsigned short, 1><<<dim3(gx, ny), kColThreads, 0, st>>>(
         s->Y, c16, s->G.p, s->order.p, m->ratio.p, s->R.p, m->u.p, m->act_cur.p, s->L, m->N, chunk,
@@ -740,11 +755,10 @@ int ursm_mle_opt_step(ursm_mle* mm, const double* d_cconst_part, void* stream) {
   }
   mle_cand_kernel<<<dim3(ncand, m->K), T, dyn, st>>>(a);
   URSM_LAUNCH_CHECK();
-  mle_decide_kernel<<<1, 32, 0, st>>>(m->cres.p, m->act_cur.p, m->act_next.p, m->niter.p,
-                                      m->base.p, m->halv.p, m->delta.p, m->win.p, m->K, m->conv,
-                                      m->maxiter, ncand);
-  URSM_LAUNCH_CHECK();
-  mle_copy_kernel<<<dim3(m->K, 8), 256, 0, st>>>(m->A.p, m->cand.p, m->win.p, m->N);
+  const int Tc = std::max(64, std::min(1024, (m->N / 4 + 31) / 32 * 32));
+  mle_decide_copy_kernel<<<m->K, Tc, 0, st>>>(m->cres.p, m->act_cur.p, m->act_next.p, m->niter.p,
+                                             m->base.p, m->halv.p, m->delta.p, m->A.p, m->cand.p,
+                                             m->N, m->conv, m->maxiter, ncand);
   URSM_LAUNCH_CHECK();
   URSM_API_END
 }
@@ -765,8 +779,7 @@ int ursm_mle_opt_merge(ursm_mle* mm, const double* d_part_local, double* d_part,
   mle_merge_kernel<<<dim3((m->N + 255) / 256, m->K + 1), 256, 0, st>>>(d_part_local, d_part,
                                                                        m->act_cur.p, m->N, m->K);
   URSM_LAUNCH_CHECK();
-  mle_advance_kernel<<<1, 32, 0, st>>>(m->act_cur.p, m->act_next.p, m->K);
-  URSM_LAUNCH_CHECK();
+  std::swap(m->act_cur.p, m->act_next.p);  // advance: the flags decided in this iteration
   URSM_API_END
 }
 
