@@ -174,23 +174,26 @@ mle_colsum_kernel(const float* Y, const CT* cnt, const int* G, const int* order,
 // (one 4- or 8-byte counter load per cell), kUDepth steps in flight.  A is read from L2
 // once per CTA and run instead of once per cell; counter -> double is a byte permute and
 // one DADD (small_uint_to_double).
-constexpr int kURows = 4, kUDepth = 2, kUThreads = 256;
+constexpr int kURows = 4, kUDepth = 4, kUThreads = 256;
 constexpr int kUSegGenes = 4096;  // genes per segment: 32 KB of A in shared memory
 
+// four adjacent counters as one raw 4- or 8-byte load (kept packed while in flight)
 template <class CT>
-__device__ __forceinline__ void load4(const CT* p, unsigned int (&c)[4]) {
-  if constexpr (sizeof(CT) == 1) {
-    const unsigned int v = *reinterpret_cast<const unsigned int*>(p);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) c[r] = __byte_perm(v, 0u, 0x4440 + r);
-  } else {
-    const uint2 v = *reinterpret_cast<const uint2*>(p);
-    c[0] = __byte_perm(v.x, 0u, 0x4410);
-    c[1] = __byte_perm(v.x, 0u, 0x4432);
-    c[2] = __byte_perm(v.y, 0u, 0x4410);
-    c[3] = __byte_perm(v.y, 0u, 0x4432);
+struct Raw4 {
+  uint2 v;
+  __device__ __forceinline__ void load(const CT* p) {
+    if constexpr (sizeof(CT) == 1) {
+      v.x = *reinterpret_cast<const unsigned int*>(p);
+      v.y = 0u;
+    } else {
+      v = *reinterpret_cast<const uint2*>(p);
+    }
   }
-}
+  __device__ __forceinline__ double get(int r) const {
+    if constexpr (sizeof(CT) == 1) return small_uint_to_double(__byte_perm(v.x, 0u, 0x4440 + r));
+    return small_uint_to_double(__byte_perm(r < 2 ? v.x : v.y, 0u, (r & 1) ? 0x4432 : 0x4410));
+  }
+};
 
 template <class CT>
 __global__ void __launch_bounds__(kUThreads)
@@ -230,12 +233,12 @@ mle_u_kernel(const CT* cnt, const int* order, const int* type_start, const doubl
 #pragma unroll
         for (int q = 0; q < kURows; ++q) row[q] = cnt + (size_t)(l[q] >= 0 ? l[q] : l[0]) * N + g_lo;
         for (int v0 = lane; v0 < nv; v0 += 32 * kUDepth) {
-          unsigned int c[kUDepth][kURows][4];
+          Raw4<CT> c[kUDepth][kURows];
 #pragma unroll
           for (int t = 0; t < kUDepth; ++t) {
             const int v = min(v0 + 32 * t, nv - 1);  // clamped; out-of-range steps are skipped
 #pragma unroll
-            for (int q = 0; q < kURows; ++q) load4<CT>(row[q] + 4 * (size_t)v, c[t][q]);
+            for (int q = 0; q < kURows; ++q) c[t][q].load(row[q] + 4 * (size_t)v);
           }
 #pragma unroll
           for (int t = 0; t < kUDepth; ++t) {
@@ -244,10 +247,10 @@ mle_u_kernel(const CT* cnt, const int* order, const int* type_start, const doubl
             const double2 a01 = A01[v], a23 = A23[v];
 #pragma unroll
             for (int q = 0; q < kURows; ++q) {
-              s[q] = fma(a01.x, small_uint_to_double(c[t][q][0]), s[q]);
-              s[q] = fma(a01.y, small_uint_to_double(c[t][q][1]), s[q]);
-              s[q] = fma(a23.x, small_uint_to_double(c[t][q][2]), s[q]);
-              s[q] = fma(a23.y, small_uint_to_double(c[t][q][3]), s[q]);
+              s[q] = fma(a01.x, c[t][q].get(0), s[q]);
+              s[q] = fma(a01.y, c[t][q].get(1), s[q]);
+              s[q] = fma(a23.x, c[t][q].get(2), s[q]);
+              s[q] = fma(a23.y, c[t][q].get(3), s[q]);
             }
           }
         }
