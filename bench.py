@@ -11,9 +11,10 @@ updates: (L*N + M*N) * (burnin + sample*thin) per step.
 
   value     updates of all ranks / device time of the K timed steps, inputs resident in
             HBM (weak scaling: every rank holds one copy of the workload's rows)
-  e2e       the same metric through the public API from HOST buffers: every step
-            uploads the count matrices (pinned host memory), runs the EM iteration and
-            reads A / alpha / pkappa / ptau / E[kappa] / E[tau] / E[W] / E[S] back
+  e2e       the same metric through the public API from HOST buffers, at any rank count:
+            every step builds LogitNormalGEM from the rank's pinned host count matrices
+            (upload), runs the EM iteration and reads A / alpha / E[kappa] / E[tau] /
+            E[W] / E[Z] / E[S] back to host arrays; wall clock, max over ranks
   roofline  the single-cell Gibbs kernel against the measured HBM peak, using the
             algorithmic bytes per update of SURVEY 8d / DESIGN.md
   cpu_baseline   the CPU oracle (numpy restatement of the reference + compiled PG

@@ -12,7 +12,7 @@ for multi-GPU sharding and reproducibility.
 Differences that a caller can observe (all deliberate):
   * the chain state (psi, w, S, Z, AW) never exists on the host; `suff_stats`
     holds the reference's keys, with `exp_S` materialised lazily from the
-    device-resident uint16 counters when somebody reads it;
+    device-resident 8- or 16-bit counters when somebody reads it;
   * random numbers come from counter-based Philox keyed on (seed, EM iteration,
     global cell/sample index, gene, sweep) instead of the unseeded global numpy
     state, so the chains of an E-step depend only on (seed, parameters, data) and not on
@@ -31,7 +31,7 @@ _DEFAULT_SEED = 20171106
 
 class DeviceExpS(object):
     """`suff_stats["exp_S"]` (L x N, e_step_gibbs.py:232,247): a lazy view of the
-    uint16 counters that stay on the device (local shard rows)."""
+    8- or 16-bit counters that stay on the device (local shard rows)."""
 
     def __init__(self, sampler):
         self._sampler = sampler
