@@ -166,6 +166,18 @@ int ursm_mle_opt_begin(ursm_mle* m, const int32_t* h_active, double init_step, d
 int ursm_mle_opt_step(ursm_mle* m, const double* d_cconst_part, void* stream);
 int ursm_mle_opt_pass(ursm_mle* m, double* d_part_local, void* stream);
 int ursm_mle_opt_merge(ursm_mle* m, const double* d_part_local, double* d_part, void* stream);
+/* The per-iteration cross-rank sum of `pass` + `merge` (N*K + K doubles per outer
+ * iteration of opt_Ak) without a collective call: each rank's partials live in an IPC-shared
+ * block (ursm_mle_p2p_alloc returns its 64-byte cudaIpcMemHandle_t; the caller exchanges the
+ * handles, ursm_mle_p2p_open maps the peers'), `pass_p2p` writes them there and `merge_p2p`
+ * is ONE kernel that signals the peers, waits for them and installs the rank-ordered sum read
+ * over NVLink.  ursm_mle_p2p_error reports a peer that never showed up (the kernel gives up
+ * after ~2 s instead of hanging). */
+int ursm_mle_p2p_alloc(ursm_mle* m, void* out_handle64);
+int ursm_mle_p2p_open(ursm_mle* m, const void* handles, int32_t world, int32_t rank);
+int ursm_mle_opt_pass_p2p(ursm_mle* m, void* stream);
+int ursm_mle_opt_merge_p2p(ursm_mle* m, double* d_part, void* stream);
+int ursm_mle_p2p_error(ursm_mle* m, int32_t* h_err);
 int ursm_mle_opt_poll(ursm_mle* m, int32_t* h_active, int32_t* h_niter, int32_t* h_halvings,
                       double* h_delta, void* stream);
 int ursm_mle_closed_form(ursm_mle* m, int32_t k, const double* d_exp_Zik, void* stream);

@@ -1,0 +1,70 @@
+"""Two-rank runs on one box (skipped when fewer than two GPUs are visible): the M-step's
+per-iteration cross-rank sum over NVLink peer memory (ursm_mle_opt_merge_p2p) must give the
+same fit as the NCCL all-reduce path, and a sharded fit the same estimates as one rank."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import json, os, sys
+import numpy as np
+import torch, torch.distributed as td
+sys.path.insert(0, %(root)r)
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+    td.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+from oracle import ursm_oracle as orc
+from ursm_b200.gem import LogitNormalGEM
+sim = orc.simulate(N=400, K=3, L=90, M=12, seed=5)
+gem = LogitNormalGEM(BKexpr=sim["X"], SCexpr=sim["Y"], K=3, G=sim["G"], burnin=10, sample=20,
+                     thin=1, bk_mean_approx=True, MLE_CONV=1e-6, MLE_maxiter=60, EM_CONV=1e-9,
+                     EM_maxiter=3, seed=9)
+niter, elbo, conv, path = gem.gem()
+if int(os.environ.get("RANK", "0")) == 0:
+    print("RESULT " + json.dumps({"path": [float(x) for x in path], "A": gem.A.tolist(),
+                                  "p2p": bool(getattr(gem.mle, "_p2p", False))}))
+if world > 1:
+    td.destroy_process_group()
+"""
+
+
+def _run(nproc, env_extra):
+    import torch
+    env = dict(os.environ)
+    env.update(env_extra)
+    code = WORKER % {"root": ROOT}
+    if nproc == 1:
+        cmd = [sys.executable, "-c", code]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+               str(nproc), "--master-addr", "127.0.0.1", "--master-port", "29611", "--no-python",
+               sys.executable, "-c", code]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.loads(line[len("RESULT "):])
+
+
+def test_two_ranks_peer_exchange_matches_nccl_and_single_rank():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    one = _run(1, {})
+    p2p = _run(2, {"URSM_MLE_P2P": "1"})
+    nccl = _run(2, {"URSM_MLE_P2P": "0"})
+    assert p2p["p2p"] and not nccl["p2p"]
+    # chains do not depend on the sharding; the statistics are summed in a different order
+    for other in (p2p, nccl):
+        np.testing.assert_allclose(other["path"], one["path"], rtol=2e-5)
+        np.testing.assert_allclose(other["A"], one["A"], rtol=5e-3, atol=1e-7)
+    np.testing.assert_allclose(p2p["path"], nccl["path"], rtol=2e-5)

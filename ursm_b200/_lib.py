@@ -62,6 +62,11 @@ SIGNATURES = {
     "ursm_mle_opt_pass": (c_int, [c_vp, c_vp, c_vp]),
     "ursm_mle_opt_merge": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_opt_poll": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ursm_mle_p2p_alloc": (c_int, [c_vp, c_vp]),
+    "ursm_mle_p2p_open": (c_int, [c_vp, c_vp, c_i32, c_i32]),
+    "ursm_mle_opt_pass_p2p": (c_int, [c_vp, c_vp]),
+    "ursm_mle_opt_merge_p2p": (c_int, [c_vp, c_vp, c_vp]),
+    "ursm_mle_p2p_error": (c_int, [c_vp, c_vp]),
     "ursm_mle_closed_form": (c_int, [c_vp, c_i32, c_vp, c_vp]),
     "ursm_mle_elbo_terms": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_get_u": (c_int, [c_vp, c_vp]),

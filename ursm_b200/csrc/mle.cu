@@ -20,6 +20,8 @@
 
 namespace ursm {
 
+constexpr int kMaxPeers = 16;  // ranks of one NVLink domain that exchange partials directly
+
 struct Mle {
   ScShard* sc = nullptr;
   BkShard* bk = nullptr;
@@ -40,6 +42,19 @@ struct Mle {
   double init_step = 0, conv = 0;
   int maxiter = 0;
   int num_sms = 148;
+  // peer-memory exchange of the per-iteration partials (ursm_mle_p2p_*): one cudaMalloc'd,
+  // IPC-shared block per rank = two (KN + K)-double buffers + one epoch word per peer
+  void* p2p_own = nullptr;
+  void* p2p_peer[kMaxPeers] = {nullptr};
+  int p2p_world = 0, p2p_rank = 0;
+  unsigned long long p2p_epoch = 0;
+  int* p2p_err = nullptr;  // device flag: a peer did not show up in time
+  ~Mle() {
+    for (int r = 0; r < p2p_world; ++r)
+      if (r != p2p_rank && p2p_peer[r]) cudaIpcCloseMemHandle(p2p_peer[r]);
+    if (p2p_own) cudaFree(p2p_own);
+    if (p2p_err) cudaFree(p2p_err);
+  }
 };
 
 constexpr int kCand = 16;  // trial step sizes of backtracking evaluated concurrently
@@ -471,6 +486,70 @@ __global__ void mle_merge_kernel(const double* part_local, double* part, const i
   if (i < N) part[(size_t)k * N + i] = part_local[(size_t)k * N + i];
 }
 
+// The same installation fused with the cross-rank sum (one all-reduce of
+// N*K + K doubles per outer iteration), over NVLink peer memory instead of a collective
+// call.  Every rank's partials sit in an IPC-shared buffer (double-buffered by epoch);
+// the first CTA of this kernel publishes "my buffer of this epoch is complete" to every
+// peer's flag word, every CTA waits until all peers have done so, then each element is
+// the sum of the W peer buffers read in rank order -- bit-identical on every rank, so the
+// replicated loop state cannot diverge.  No second barrier: a buffer is reused two epochs
+// later, by which time every peer has passed the next epoch's barrier, i.e. finished this one.
+struct P2PArgs {
+  const double* peer[kMaxPeers];        // peer r's buffer of this epoch
+  unsigned long long* peer_flags[kMaxPeers];  // peer r's flag array (we write entry `rank`)
+  const unsigned long long* my_flags;   // [world] written by the peers
+  int world, rank;
+  unsigned long long epoch;
+  int* err;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void mle_p2p_merge_kernel(P2PArgs a, double* part, const int* act, int N, int K) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(a.peer_flags[threadIdx.x] + a.rank, a.epoch);
+  }
+  if ((int)threadIdx.x < a.world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(a.my_flags + threadIdx.x) < a.epoch) {
+      if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone; fail loudly instead of hanging
+        *a.err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const int k = blockIdx.y;
+  if (k == K) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < K) {
+      double s = 0.0;
+      for (int r = 0; r < a.world; ++r) s += ld_relaxed_sys(a.peer[r] + (size_t)K * N + threadIdx.x);
+      part[(size_t)K * N + threadIdx.x] = s;
+    }
+    return;
+  }
+  if (!act[k]) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    double s = 0.0;
+    for (int r = 0; r < a.world; ++r) s += ld_relaxed_sys(a.peer[r] + (size_t)k * N + i);
+    part[(size_t)k * N + i] = s;
+  }
+}
+
 // A_k = simplex_proj(v / sum v)   (m_step.py:149-153, utils.py:8-31)
 __global__ void __launch_bounds__(1024)
 mle_project_kernel(const double* v, double* y, double* out, int N, double m, int normalise) {
@@ -783,6 +862,96 @@ int ursm_mle_opt_merge(ursm_mle* mm, const double* d_part_local, double* d_part,
                                                                        m->act_cur.p, m->N, m->K);
   URSM_LAUNCH_CHECK();
   std::swap(m->act_cur.p, m->act_next.p);  // advance: the flags decided in this iteration
+  URSM_API_END
+}
+
+static size_t p2p_buf_doubles(const Mle* m) { return (size_t)m->K * m->N + m->K; }
+static size_t p2p_bytes(const Mle* m) {
+  return 2 * p2p_buf_doubles(m) * sizeof(double) + kMaxPeers * sizeof(unsigned long long);
+}
+static double* p2p_buf(const Mle* m, void* base, unsigned long long epoch) {
+  return static_cast<double*>(base) + (epoch & 1ull) * p2p_buf_doubles(m);
+}
+static unsigned long long* p2p_flags(const Mle* m, void* base) {
+  return reinterpret_cast<unsigned long long*>(static_cast<double*>(base) + 2 * p2p_buf_doubles(m));
+}
+
+int ursm_mle_p2p_alloc(ursm_mle* mm, void* out_handle64) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && out_handle64, "ursm_mle_p2p_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!m->p2p_own) {
+    URSM_CUDA(cudaMalloc(&m->p2p_own, p2p_bytes(m)));  // IPC needs a cudaMalloc block, not the pool
+    URSM_CUDA(cudaMemset(m->p2p_own, 0, p2p_bytes(m)));
+    URSM_CUDA(cudaMalloc((void**)&m->p2p_err, sizeof(int)));
+    URSM_CUDA(cudaMemset(m->p2p_err, 0, sizeof(int)));
+    URSM_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  URSM_CUDA(cudaIpcGetMemHandle(&h, m->p2p_own));
+  memcpy(out_handle64, &h, sizeof h);
+  URSM_API_END
+}
+
+int ursm_mle_p2p_open(ursm_mle* mm, const void* handles, int32_t world, int32_t rank) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && handles && m->p2p_own, "ursm_mle_p2p_open: call ursm_mle_p2p_alloc first");
+  URSM_REQUIRE(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world,
+               "ursm_mle_p2p_open: bad world/rank");
+  const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      m->p2p_peer[r] = m->p2p_own;
+    } else {
+      URSM_CUDA(cudaIpcOpenMemHandle(&m->p2p_peer[r], hs[r], cudaIpcMemLazyEnablePeerAccess));
+    }
+  }
+  m->p2p_world = world;
+  m->p2p_rank = rank;
+  m->p2p_epoch = 0;
+  URSM_API_END
+}
+
+int ursm_mle_opt_pass_p2p(ursm_mle* mm, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && m->sc && m->p2p_world >= 2, "ursm_mle_opt_pass_p2p: peer exchange not set up");
+  ++m->p2p_epoch;
+  mle_pass(m, p2p_buf(m, m->p2p_own, m->p2p_epoch), (cudaStream_t)stream);
+  URSM_API_END
+}
+
+int ursm_mle_opt_merge_p2p(ursm_mle* mm, double* d_part, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && d_part && m->p2p_world >= 2, "ursm_mle_opt_merge_p2p: peer exchange not set up");
+  cudaStream_t st = (cudaStream_t)stream;
+  P2PArgs a;
+  memset(&a, 0, sizeof a);
+  for (int r = 0; r < m->p2p_world; ++r) {
+    a.peer[r] = p2p_buf(m, m->p2p_peer[r], m->p2p_epoch);
+    a.peer_flags[r] = p2p_flags(m, m->p2p_peer[r]);
+  }
+  a.my_flags = p2p_flags(m, m->p2p_own);
+  a.world = m->p2p_world;
+  a.rank = m->p2p_rank;
+  a.epoch = m->p2p_epoch;
+  a.err = m->p2p_err;
+  mle_p2p_merge_kernel<<<dim3((m->N + 255) / 256, m->K + 1), 256, 0, st>>>(a, d_part, m->act_cur.p,
+                                                                           m->N, m->K);
+  URSM_LAUNCH_CHECK();
+  std::swap(m->act_cur.p, m->act_next.p);  // advance: the flags decided in this iteration
+  URSM_API_END
+}
+
+int ursm_mle_p2p_error(ursm_mle* mm, int32_t* h_err) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && h_err, "ursm_mle_p2p_error: bad argument");
+  *h_err = 0;
+  if (m->p2p_err) URSM_CUDA(cudaMemcpy(h_err, m->p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
   URSM_API_END
 }
 

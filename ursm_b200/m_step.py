@@ -79,6 +79,41 @@ class LogitNormalMLE(object):
         self._zik = torch.zeros(KN, **f)
         _lib.call("ursm_mle_set_coeffs", self._h, self._p(self._cAinv), self._p(self._cA),
                   self._p(self._coeffA))
+        self._p2p = self._setup_p2p() if sc is not None else False
+
+    def _setup_p2p(self):
+        """Peer-memory exchange for the per-iteration sum of opt_Ak (one NVLink domain, NCCL
+        backend): every rank shares one IPC block, the handles travel once through
+        torch.distributed.  `URSM_MLE_P2P=0` keeps the NCCL all-reduce (A/B measurements)."""
+        import os
+        import torch
+        import torch.distributed as td
+        world = dist.world_size()
+        if world < 2 or world > 16 or os.environ.get("URSM_MLE_P2P", "1") == "0":
+            return False
+        if td.get_backend() != "nccl":
+            return False
+        handle = (ctypes.c_char * 64)()
+        ok = 1
+        try:
+            _lib.call("ursm_mle_p2p_alloc", self._h, ctypes.cast(handle, ctypes.c_void_p))
+        except _lib.UrsmError as e:  # pragma: no cover
+            logging.warning("peer-memory exchange unavailable (%s); using NCCL", e)
+            ok = 0
+        gathered = [None] * world
+        td.all_gather_object(gathered, (ok, bytes(handle.raw)))
+        if not all(g[0] for g in gathered):
+            return False
+        blob = b"".join(g[1] for g in gathered)
+        try:
+            _lib.call("ursm_mle_p2p_open", self._h, ctypes.c_char_p(blob), world, dist.rank())
+            ok = 1
+        except _lib.UrsmError as e:  # pragma: no cover
+            logging.warning("peer-memory exchange unavailable (%s); using NCCL", e)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        td.all_reduce(flag, op=td.ReduceOp.MIN)  # all ranks or none
+        return bool(int(flag.item()))
 
     @staticmethod
     def _p(t):
@@ -200,17 +235,29 @@ class LogitNormalMLE(object):
             it, poll_every = 0, 8
             while True:
                 _lib.call("ursm_mle_opt_step", self._h, self._p(self._part), st)
-                _lib.call("ursm_mle_opt_pass", self._h, self._p(self._part_local), st)
-                if multi:  # N*K + K values per outer iteration
-                    dist.all_reduce_(self._part_local)
-                _lib.call("ursm_mle_opt_merge", self._h, self._p(self._part_local),
-                          self._p(self._part), st)
+                if self._p2p:
+                    # N*K + K values per outer iteration, summed over NVLink peer
+                    # memory inside the merge kernel -- no collective call
+                    _lib.call("ursm_mle_opt_pass_p2p", self._h, st)
+                    _lib.call("ursm_mle_opt_merge_p2p", self._h, self._p(self._part), st)
+                else:
+                    _lib.call("ursm_mle_opt_pass", self._h, self._p(self._part_local), st)
+                    if multi:
+                        dist.all_reduce_(self._part_local)
+                    _lib.call("ursm_mle_opt_merge", self._h, self._p(self._part_local),
+                              self._p(self._part), st)
                 it += 1
                 if it % poll_every == 0:
                     _lib.call("ursm_mle_opt_poll", self._h, _lib.ptr(active), _lib.ptr(niter),
                               _lib.ptr(halv), None, st)
                     if not active.any():
                         break
+            if self._p2p:
+                err = ctypes.c_int32(0)
+                _lib.call("ursm_mle_p2p_error", self._h, ctypes.byref(err))
+                if err.value:
+                    raise _lib.UrsmError("M-step peer exchange: a rank did not reach the "
+                                         "iteration barrier (timeout)")
             self.niter_A[:] = niter
             self.nhalvings += int(halv.sum())
             for k in range(K):
