@@ -463,6 +463,7 @@ def gpu_main(args, cfg):
         "s_per_em_iter": dev_ms / args.steps / 1e3, "wall_ms_per_step": wall_ms / args.steps,
         "kernel_ms": {"sc_gibbs": float(np.mean(sc_ms)) if sc_ms else None,
                       "bk_estep": float(np.mean(bk_ms)) if bk_ms else None},
+        "sc_geometry": gem.Gibbs_SC.geometry() if gem.hasSC else None,
         "elbo_last": elbo, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,
     }

@@ -527,50 +527,64 @@ void upload_f64_as_f32(const double* h, float* d, size_t n) {
   URSM_CUDA(cudaDeviceSynchronize());
 }
 
+// Shared memory of one CTA with T threads x g genes per thread: reductions / broadcast /
+// normal pairs, then per gene slot 10 bytes (w, threshold, E[S] counter) + 8 for in-smem
+// accumulators, and one S bit mask per thread.
+static size_t sc_smem_bytes(int T, int g, bool acc_smem) {
+  const size_t fixed = (32 + 64 + 96 + 2 * kNormChunk + 4) * 8 + (64 + 4) * 4 + (size_t)T * 4;
+  return fixed + (size_t)T * g * (acc_smem ? 18 : 10) + 16;
+}
+
+// Geometry: the kernel is bound by dependent-instruction latency, not by instruction
+// count, so what matters is resident warps per SM (64 registers per thread and the
+// cell's 10 B per gene of shared memory set the limit) times the fraction of lanes
+// that own genes.  Candidates: g = 8..32 genes per thread, T = ceil(N / g) rounded
+// up to a warp; ties go to the smaller CTA (cheaper barriers).
 static void sc_pick_geometry(ScShard* s) {
   s->num_sms = device_sm_count();
   const size_t smem_optin = device_smem_optin();
   int maxT = 1024;
   if (const char* e = getenv("URSM_SC_MAX_THREADS")) maxT = std::max(64, std::min(1024, atoi(e)));
-  int gpt = 16;
-  if (const char* e = getenv("URSM_SC_GENES_PER_THREAD")) gpt = std::max(1, atoi(e));
-  int T = ((s->N + gpt - 1) / gpt + 31) / 32 * 32;
-  T = std::max(64, std::min(maxT / 32 * 32, T));
-  s->T = T;
-  s->g = (s->N + T - 1) / T;
-  URSM_REQUIRE(s->g <= 32, "gene count too large for the chain-resident single-cell kernel "
-                           "(at most 32 genes per thread)");
-  // reductions / broadcast / normal pairs, then per gene slot 10 bytes (w, threshold,
-  // E[S] counter) + 8 for in-smem accumulators, and one S bit mask per thread
-  const size_t fixed = (32 + 64 + 96 + 2 * kNormChunk + 4) * 8 + (64 + 4) * 4 + (size_t)s->T * 4;
-  s->pad = 0;
-  s->slots = s->T * s->g;
-  size_t small = fixed + (size_t)s->slots * 10, big = fixed + (size_t)s->slots * 18;
+  maxT = maxT / 32 * 32;
   int acc_limit = 32 * 1024;
   if (const char* e = getenv("URSM_SC_ACC_SMEM_LIMIT")) acc_limit = atoi(e);
-  s->acc_smem = big <= (size_t)acc_limit;
-  s->smem = (int)((s->acc_smem ? big : small) + 16);
-  URSM_REQUIRE((size_t)s->smem <= smem_optin,
-               "gene count too large for the chain-resident single-cell kernel "
-               "(10 bytes of shared memory per gene)");
-  if (s->acc_smem) {
-    URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem));
-  } else {
-    URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem));
+  int g_lo = 8, g_hi = 32;
+  if (const char* e = getenv("URSM_SC_GENES_PER_THREAD")) g_lo = g_hi = std::max(1, std::min(32, atoi(e)));
+  URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_optin));
+  URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_optin));
+  double best = -1.0;
+  for (int gpt = g_lo; gpt <= g_hi; ++gpt) {
+    int T = ((s->N + gpt - 1) / gpt + 31) / 32 * 32;
+    T = std::max(64, std::min(maxT, T));
+    const int g = (s->N + T - 1) / T;
+    if (g > 32) continue;
+    const bool acc = sc_smem_bytes(T, g, true) <= (size_t)acc_limit;
+    const size_t smem = sc_smem_bytes(T, g, acc);
+    if (smem > smem_optin) continue;
+    int occ = 0;
+    if (acc) {
+      URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<true>, T, smem));
+    } else {
+      URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<false>, T, smem));
+    }
+    if (occ < 1) continue;
+    const double score = (double)occ * (T / 32) * ((double)s->N / ((double)T * g));
+    if (score > best * (1.0 + 1e-9) || (score > best * (1.0 - 1e-9) && T < s->T)) {
+      best = score;
+      s->T = T;
+      s->g = g;
+      s->acc_smem = acc;
+      s->smem = (int)smem;
+      s->occ = occ;
+    }
   }
-  int occ = 0;
-  if (s->acc_smem) {
-    URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<true>, s->T,
-                                                            s->smem));
-  } else {
-    URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<false>, s->T,
-                                                            s->smem));
-  }
-  URSM_REQUIRE(occ >= 1, "single-cell Gibbs kernel does not fit on an SM");
-  s->occ = occ;
-  long long want = (long long)s->num_sms * occ;
+  URSM_REQUIRE(best > 0.0, "gene count too large for the chain-resident single-cell kernel "
+                           "(10 bytes of shared memory per gene, at most 32 genes per thread)");
+  s->pad = 0;
+  s->slots = s->T * s->g;
+  long long want = (long long)s->num_sms * s->occ;
   s->grid = (int)std::max<long long>(1, std::min<long long>(want, s->L));
   if (!s->acc_smem) s->scratch.alloc((size_t)s->grid * 2 * s->slots);
 }
