@@ -255,7 +255,11 @@ static void bk_launch_split(BkShard* b, BkTileArgs& a, cudaStream_t st) {
   const int gx = (b->N + kSplitThreads - 1) / kSplitThreads;
   // a chunk's W rows and per-sample sums (8 B per sample and type): at most 24 KB of smem
   const long long max_chunk = std::max<long long>(1, (long long)(24 * 1024) / (8 * (long long)K));
-  long long want_y = std::max<long long>(1, (long long)(6 * b->num_sms + gx - 1) / gx);
+  // many small CTAs: the tiles differ a lot in cost (columns are sorted by depth), so the
+  // hardware scheduler needs fine grains to balance them (16 per SM measured best at c2)
+  int per_sm = 16;
+  if (const char* e = getenv("URSM_BK_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+  long long want_y = std::max<long long>(1, (long long)(per_sm * b->num_sms + gx - 1) / gx);
   want_y = std::max<long long>(want_y, (b->M + max_chunk - 1) / max_chunk);
   long long ny = std::min<long long>(b->M, want_y);
   a.chunk = (int)((b->M + ny - 1) / ny);
@@ -287,34 +291,47 @@ __global__ void bk_nmf_update_kernel(double* W, const double* numer, const doubl
 }
 
 // One Gibbs sweep's W step (:140-146) plus the per-sample part of update_suffStats.
-__global__ void bk_w_draw_kernel(double* W, const double* n_prev, double* n_next,
-                                 const double* alpha, long long M, int K, long long sample_offset,
-                                 unsigned long long key, unsigned int sweep, int prev_retained,
-                                 int retained, int draw, double inv_sample, double* eZjk,
-                                 double* eLogW, double* eW) {
-  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= M) return;
-  if (prev_retained)
-    for (int k = 0; k < K; ++k) eZjk[j * K + k] += n_prev[j * K + k] * inv_sample;
+// One thread per (sample, type): W_j ~ Dir(alpha + sum_i Z_j.) is K independent gammas
+// (each from its own Philox stream, keyed on the global sample id and the type) that the
+// sample's K threads then normalise through shared memory in a fixed order.
+constexpr int kWDrawThreads = 128;
+
+__global__ void __launch_bounds__(kWDrawThreads)
+bk_w_draw_kernel(double* W, const double* n_prev, double* n_next, const double* alpha,
+                 long long M, int K, long long sample_offset, unsigned long long key,
+                 unsigned int sweep, int prev_retained, int retained, int draw,
+                 double inv_sample, double* eZjk, double* eLogW, double* eW) {
+  __shared__ double g_s[kWDrawThreads];
+  const int per_block = kWDrawThreads / K;  // samples per CTA
+  const int jl = threadIdx.x / K, k = threadIdx.x - jl * K;
+  const long long j = (long long)blockIdx.x * per_block + jl;
+  const bool on = jl < per_block && j < M;
+  const size_t e = on ? (size_t)j * K + k : 0;
+  double gmm = 0.0;
+  if (on) {
+    if (prev_retained) eZjk[e] += n_prev[e] * inv_sample;
+    if (draw) {
+      Philox rng(key, 0xfffffffeu - (uint32_t)k, (uint32_t)(sample_offset + j), kPurposeBulkW | sweep);
+      gmm = gamma_mt(alpha[k] + n_prev[e], rng);
+    }
+  }
   if (draw) {
-    Philox rng(key, 0xfffffffeu, (uint32_t)(sample_offset + j), kPurposeBulkW | sweep);
-    double s = 0.0;
-    for (int k = 0; k < K; ++k) {
-      double gmm = gamma_mt(alpha[k] + n_prev[j * K + k], rng);
-      W[j * K + k] = gmm;
-      s += gmm;
-    }
-    for (int k = 0; k < K; ++k) W[j * K + k] /= s;
-  }
-  if (retained) {
-    for (int k = 0; k < K; ++k) {
-      double w = W[j * K + k];
-      eW[j * K + k] += w * inv_sample;
-      eLogW[j * K + k] += log(w) * inv_sample;
+    g_s[threadIdx.x] = gmm;
+    __syncthreads();
+    if (on) {
+      double s = 0.0;
+      for (int q = 0; q < K; ++q) s += g_s[jl * K + q];
+      W[e] = gmm / s;
     }
   }
-  if (n_next)
-    for (int k = 0; k < K; ++k) n_next[j * K + k] = 0.0;
+  if (on) {
+    if (retained) {
+      const double w = W[e];
+      eW[e] += w * inv_sample;
+      eLogW[e] += log(w) * inv_sample;
+    }
+    if (n_next) n_next[e] = 0.0;
+  }
 }
 
 __global__ void bk_mean_finalize_kernel(const double* W, double* eLogW, double* eW, long long M,
@@ -595,7 +612,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   URSM_REQUIRE(burnin >= 0 && sample >= 1 && thin >= 1, "ursm_bk_gibbs: bad sweep counts");
   if (!b->Xs.p) bk_build_sorted(b);  // once per fit, first Gibbs E-step only
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned mb = (unsigned)((b->M + 127) / 128);
+  const unsigned mb = (unsigned)((b->M + (kWDrawThreads / b->K) - 1) / (kWDrawThreads / b->K));
   const unsigned long long key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1) + 0x5bd1e995ull;
   const PhiloxKeys rk = philox_keys(key);
   const double inv = 1.0 / sample;
@@ -610,7 +627,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   for (int sweep = 0; sweep < nsweeps; ++sweep) {
     const bool retained = sweep >= burnin && ((sweep - burnin) % thin == 0);
     const bool freezeW = freeze & 1, freezeZ = freeze & 2;
-    bk_w_draw_kernel<<<mb, 128, 0, st>>>(b->W.p, b->nA.p, b->nB.p, b->alpha.p, b->M, b->K,
+    bk_w_draw_kernel<<<mb, kWDrawThreads, 0, st>>>(b->W.p, b->nA.p, b->nB.p, b->alpha.p, b->M, b->K,
                                          b->sample_offset, key, (unsigned)sweep, prev_ret ? 1 : 0,
                                          retained ? 1 : 0, freezeW ? 0 : 1, inv, b->eZjk.p,
                                          b->eLogW.p, b->eW.p);
@@ -632,7 +649,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
     prev_ret = retained;
   }
   // the last retained sweep's sum_i Z
-  bk_w_draw_kernel<<<mb, 128, 0, st>>>(b->W.p, b->nA.p, nullptr, b->alpha.p, b->M, b->K,
+  bk_w_draw_kernel<<<mb, kWDrawThreads, 0, st>>>(b->W.p, b->nA.p, nullptr, b->alpha.p, b->M, b->K,
                                        b->sample_offset, key, 0u, prev_ret ? 1 : 0, 0, 0, inv,
                                        b->eZjk.p, b->eLogW.p, b->eW.p);
   URSM_LAUNCH_CHECK();
