@@ -294,6 +294,9 @@ def gpu_main(args, cfg):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its debug output (the version banner included) to stdout by default,
+        # next to the JSON line: send it to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     from ursm_b200 import _lib, synth
     from ursm_b200.gem import LogitNormalGEM

@@ -171,9 +171,12 @@ int ursm_mle_opt_merge(ursm_mle* m, const double* d_part_local, double* d_part, 
  * block (ursm_mle_p2p_alloc returns its 64-byte cudaIpcMemHandle_t; the caller exchanges the
  * handles, ursm_mle_p2p_open maps the peers'), `pass_p2p` writes them there and `merge_p2p`
  * is ONE kernel that signals the peers, waits for them and installs the rank-ordered sum read
- * over NVLink.  ursm_mle_p2p_error reports a peer that never showed up (the kernel gives up
- * after ~2 s instead of hanging). */
-int ursm_mle_p2p_alloc(ursm_mle* m, void* out_handle64);
+ * over NVLink.  Blocks and their peer mappings are cached per process by size (`out_cached`:
+ * this rank already holds the mappings; when every rank says so `open` needs no handles).
+ * ursm_mle_p2p_error reports a peer that never showed up (the kernel gives up after ~2 s
+ * instead of hanging). */
+int ursm_mle_p2p_alloc(ursm_mle* m, void* out_handle64, int32_t* out_cached);
+int ursm_mle_p2p_disable(ursm_mle* m);
 int ursm_mle_p2p_open(ursm_mle* m, const void* handles, int32_t world, int32_t rank);
 int ursm_mle_opt_pass_p2p(ursm_mle* m, void* stream);
 int ursm_mle_opt_merge_p2p(ursm_mle* m, double* d_part, void* stream);

@@ -62,7 +62,8 @@ SIGNATURES = {
     "ursm_mle_opt_pass": (c_int, [c_vp, c_vp, c_vp]),
     "ursm_mle_opt_merge": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_opt_poll": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "ursm_mle_p2p_alloc": (c_int, [c_vp, c_vp]),
+    "ursm_mle_p2p_alloc": (c_int, [c_vp, c_vp, c_vp]),
+    "ursm_mle_p2p_disable": (c_int, [c_vp]),
     "ursm_mle_p2p_open": (c_int, [c_vp, c_vp, c_i32, c_i32]),
     "ursm_mle_opt_pass_p2p": (c_int, [c_vp, c_vp]),
     "ursm_mle_opt_merge_p2p": (c_int, [c_vp, c_vp, c_vp]),

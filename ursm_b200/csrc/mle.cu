@@ -17,6 +17,7 @@
 #include "../../include/ursm_b200.h"
 
 #include <algorithm>
+#include <vector>
 
 namespace ursm {
 
@@ -42,20 +43,30 @@ struct Mle {
   double init_step = 0, conv = 0;
   int maxiter = 0;
   int num_sms = 148;
-  // peer-memory exchange of the per-iteration partials (ursm_mle_p2p_*): one cudaMalloc'd,
-  // IPC-shared block per rank = two (KN + K)-double buffers + one epoch word per peer
-  void* p2p_own = nullptr;
-  void* p2p_peer[kMaxPeers] = {nullptr};
-  int p2p_world = 0, p2p_rank = 0;
-  unsigned long long p2p_epoch = 0;
-  int* p2p_err = nullptr;  // device flag: a peer did not show up in time
-  ~Mle() {
-    for (int r = 0; r < p2p_world; ++r)
-      if (r != p2p_rank && p2p_peer[r]) cudaIpcCloseMemHandle(p2p_peer[r]);
-    if (p2p_own) cudaFree(p2p_own);
-    if (p2p_err) cudaFree(p2p_err);
-  }
+  // peer-memory exchange of the per-iteration partials (ursm_mle_p2p_*)
+  struct P2PBlock* p2p = nullptr;
+  ~Mle();
 };
+
+// One cudaMalloc'd, IPC-shared block per rank = two (KN + K)-double buffers + one epoch
+// word per peer, with the peers' mappings.  Blocks are cached for the life of the process,
+// keyed by size: the reference's API builds a new M-step object per fit, and mapping seven
+// peers' handles costs milliseconds each.  The epoch counter lives with the block, so it
+// stays monotonic across the workspaces that use it one after the other.
+struct P2PBlock {
+  size_t bytes = 0;
+  void* own = nullptr;
+  void* peer[kMaxPeers] = {nullptr};
+  int world = 0, rank = 0;
+  unsigned long long epoch = 0;
+  int* err = nullptr;
+  bool opened = false, in_use = false;
+};
+static std::vector<P2PBlock*> g_p2p_blocks;
+
+Mle::~Mle() {
+  if (p2p) p2p->in_use = false;
+}
 
 constexpr int kCand = 16;  // trial step sizes of backtracking evaluated concurrently
 
@@ -876,20 +887,34 @@ static unsigned long long* p2p_flags(const Mle* m, void* base) {
   return reinterpret_cast<unsigned long long*>(static_cast<double*>(base) + 2 * p2p_buf_doubles(m));
 }
 
-int ursm_mle_p2p_alloc(ursm_mle* mm, void* out_handle64) {
+int ursm_mle_p2p_alloc(ursm_mle* mm, void* out_handle64, int32_t* out_cached) {
   URSM_API_BEGIN
   Mle* m = reinterpret_cast<Mle*>(mm);
-  URSM_REQUIRE(m && out_handle64, "ursm_mle_p2p_alloc: bad argument");
+  URSM_REQUIRE(m && out_handle64 && out_cached, "ursm_mle_p2p_alloc: bad argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  if (!m->p2p_own) {
-    URSM_CUDA(cudaMalloc(&m->p2p_own, p2p_bytes(m)));  // IPC needs a cudaMalloc block, not the pool
-    URSM_CUDA(cudaMemset(m->p2p_own, 0, p2p_bytes(m)));
-    URSM_CUDA(cudaMalloc((void**)&m->p2p_err, sizeof(int)));
-    URSM_CUDA(cudaMemset(m->p2p_err, 0, sizeof(int)));
-    URSM_CUDA(cudaDeviceSynchronize());
+  if (!m->p2p) {
+    const size_t bytes = p2p_bytes(m);
+    for (P2PBlock* b : g_p2p_blocks)
+      if (b->bytes == bytes && !b->in_use) {
+        m->p2p = b;
+        break;
+      }
+    if (!m->p2p) {
+      P2PBlock* b = new P2PBlock();
+      b->bytes = bytes;
+      URSM_CUDA(cudaMalloc(&b->own, bytes));  // IPC needs a cudaMalloc block, not the pool
+      URSM_CUDA(cudaMemset(b->own, 0, bytes));
+      URSM_CUDA(cudaMalloc((void**)&b->err, sizeof(int)));
+      URSM_CUDA(cudaMemset(b->err, 0, sizeof(int)));
+      URSM_CUDA(cudaDeviceSynchronize());
+      g_p2p_blocks.push_back(b);
+      m->p2p = b;
+    }
+    m->p2p->in_use = true;
   }
+  *out_cached = m->p2p->opened ? 1 : 0;
   cudaIpcMemHandle_t h;
-  URSM_CUDA(cudaIpcGetMemHandle(&h, m->p2p_own));
+  URSM_CUDA(cudaIpcGetMemHandle(&h, m->p2p->own));
   memcpy(out_handle64, &h, sizeof h);
   URSM_API_END
 }
@@ -897,48 +922,65 @@ int ursm_mle_p2p_alloc(ursm_mle* mm, void* out_handle64) {
 int ursm_mle_p2p_open(ursm_mle* mm, const void* handles, int32_t world, int32_t rank) {
   URSM_API_BEGIN
   Mle* m = reinterpret_cast<Mle*>(mm);
-  URSM_REQUIRE(m && handles && m->p2p_own, "ursm_mle_p2p_open: call ursm_mle_p2p_alloc first");
+  URSM_REQUIRE(m && m->p2p, "ursm_mle_p2p_open: call ursm_mle_p2p_alloc first");
   URSM_REQUIRE(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world,
                "ursm_mle_p2p_open: bad world/rank");
-  const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(handles);
-  for (int r = 0; r < world; ++r) {
-    if (r == rank) {
-      m->p2p_peer[r] = m->p2p_own;
-    } else {
-      URSM_CUDA(cudaIpcOpenMemHandle(&m->p2p_peer[r], hs[r], cudaIpcMemLazyEnablePeerAccess));
+  P2PBlock* b = m->p2p;
+  if (b->opened) {  // cached mapping: every rank reuses the block it used before
+    URSM_REQUIRE(b->world == world && b->rank == rank, "ursm_mle_p2p_open: cached block of another job");
+  } else {
+    URSM_REQUIRE(handles, "ursm_mle_p2p_open: no handles");
+    const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(handles);
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) {
+        b->peer[r] = b->own;
+      } else {
+        URSM_CUDA(cudaIpcOpenMemHandle(&b->peer[r], hs[r], cudaIpcMemLazyEnablePeerAccess));
+      }
     }
+    b->world = world;
+    b->rank = rank;
+    b->opened = true;
   }
-  m->p2p_world = world;
-  m->p2p_rank = rank;
-  m->p2p_epoch = 0;
+  URSM_API_END
+}
+
+int ursm_mle_p2p_disable(ursm_mle* mm) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  if (m && m->p2p) {
+    m->p2p->in_use = false;
+    m->p2p = nullptr;
+  }
   URSM_API_END
 }
 
 int ursm_mle_opt_pass_p2p(ursm_mle* mm, void* stream) {
   URSM_API_BEGIN
   Mle* m = reinterpret_cast<Mle*>(mm);
-  URSM_REQUIRE(m && m->sc && m->p2p_world >= 2, "ursm_mle_opt_pass_p2p: peer exchange not set up");
-  ++m->p2p_epoch;
-  mle_pass(m, p2p_buf(m, m->p2p_own, m->p2p_epoch), (cudaStream_t)stream);
+  URSM_REQUIRE(m && m->sc && m->p2p && m->p2p->opened, "ursm_mle_opt_pass_p2p: peer exchange not set up");
+  ++m->p2p->epoch;
+  mle_pass(m, p2p_buf(m, m->p2p->own, m->p2p->epoch), (cudaStream_t)stream);
   URSM_API_END
 }
 
 int ursm_mle_opt_merge_p2p(ursm_mle* mm, double* d_part, void* stream) {
   URSM_API_BEGIN
   Mle* m = reinterpret_cast<Mle*>(mm);
-  URSM_REQUIRE(m && d_part && m->p2p_world >= 2, "ursm_mle_opt_merge_p2p: peer exchange not set up");
+  URSM_REQUIRE(m && d_part && m->p2p && m->p2p->opened, "ursm_mle_opt_merge_p2p: peer exchange not set up");
   cudaStream_t st = (cudaStream_t)stream;
+  P2PBlock* b = m->p2p;
   P2PArgs a;
   memset(&a, 0, sizeof a);
-  for (int r = 0; r < m->p2p_world; ++r) {
-    a.peer[r] = p2p_buf(m, m->p2p_peer[r], m->p2p_epoch);
-    a.peer_flags[r] = p2p_flags(m, m->p2p_peer[r]);
+  for (int r = 0; r < b->world; ++r) {
+    a.peer[r] = p2p_buf(m, b->peer[r], b->epoch);
+    a.peer_flags[r] = p2p_flags(m, b->peer[r]);
   }
-  a.my_flags = p2p_flags(m, m->p2p_own);
-  a.world = m->p2p_world;
-  a.rank = m->p2p_rank;
-  a.epoch = m->p2p_epoch;
-  a.err = m->p2p_err;
+  a.my_flags = p2p_flags(m, b->own);
+  a.world = b->world;
+  a.rank = b->rank;
+  a.epoch = b->epoch;
+  a.err = b->err;
   mle_p2p_merge_kernel<<<dim3((m->N + 255) / 256, m->K + 1), 256, 0, st>>>(a, d_part, m->act_cur.p,
                                                                            m->N, m->K);
   URSM_LAUNCH_CHECK();
@@ -951,7 +993,8 @@ int ursm_mle_p2p_error(ursm_mle* mm, int32_t* h_err) {
   Mle* m = reinterpret_cast<Mle*>(mm);
   URSM_REQUIRE(m && h_err, "ursm_mle_p2p_error: bad argument");
   *h_err = 0;
-  if (m->p2p_err) URSM_CUDA(cudaMemcpy(h_err, m->p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (m->p2p && m->p2p->err)
+    URSM_CUDA(cudaMemcpy(h_err, m->p2p->err, sizeof(int), cudaMemcpyDeviceToHost));
   URSM_API_END
 }
 

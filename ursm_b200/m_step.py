@@ -94,17 +94,25 @@ class LogitNormalMLE(object):
         if td.get_backend() != "nccl":
             return False
         handle = (ctypes.c_char * 64)()
+        cached = ctypes.c_int32(0)
         ok = 1
         try:
-            _lib.call("ursm_mle_p2p_alloc", self._h, ctypes.cast(handle, ctypes.c_void_p))
+            _lib.call("ursm_mle_p2p_alloc", self._h, ctypes.cast(handle, ctypes.c_void_p),
+                      ctypes.byref(cached))
         except _lib.UrsmError as e:  # pragma: no cover
             logging.warning("peer-memory exchange unavailable (%s); using NCCL", e)
             ok = 0
+        # (ok, this rank already maps its peers, IPC handle) of every rank
         gathered = [None] * world
-        td.all_gather_object(gathered, (ok, bytes(handle.raw)))
+        td.all_gather_object(gathered, (ok, int(cached.value), bytes(handle.raw)))
         if not all(g[0] for g in gathered):
+            _lib.call("ursm_mle_p2p_disable", self._h)
             return False
-        blob = b"".join(g[1] for g in gathered)
+        n_cached = sum(g[1] for g in gathered)
+        if n_cached not in (0, world):  # ranks disagree about the cache: do not guess
+            _lib.call("ursm_mle_p2p_disable", self._h)
+            return False
+        blob = b"".join(g[2] for g in gathered)
         try:
             _lib.call("ursm_mle_p2p_open", self._h, ctypes.c_char_p(blob), world, dist.rank())
             ok = 1
@@ -113,7 +121,10 @@ class LogitNormalMLE(object):
             ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
         td.all_reduce(flag, op=td.ReduceOp.MIN)  # all ranks or none
-        return bool(int(flag.item()))
+        if not int(flag.item()):
+            _lib.call("ursm_mle_p2p_disable", self._h)
+            return False
+        return True
 
     @staticmethod
     def _p(t):
