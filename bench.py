@@ -283,7 +283,34 @@ def reference_main(args, cfg):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+class StdoutToStderr(object):
+    """Native libraries (NCCL's version banner, for one) write to file descriptor 1; the
+    contract is ONE JSON line on stdout.  Everything written to fd 1 while this is active
+    goes to stderr instead."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def gpu_main(args, cfg):
+    with StdoutToStderr():
+        line = gpu_run(args, cfg)
+    if line is not None:
+        print(json.dumps(line))
+        sys.stdout.flush()
+    return 0
+
+
+def gpu_run(args, cfg):
     import torch
     import torch.distributed as td
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,9 +321,6 @@ def gpu_main(args, cfg):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its debug output (the version banner included) to stdout by default,
-        # next to the JSON line: send it to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     from ursm_b200 import _lib, synth
     from ursm_b200.gem import LogitNormalGEM
@@ -421,7 +445,7 @@ def gpu_main(args, cfg):
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
-        return 0
+        return None
 
     peak, peak_src = load_peaks()
     roofline = None
@@ -470,10 +494,9 @@ def gpu_main(args, cfg):
         "elbo_last": elbo, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,
     }
-    print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()
-    return 0
+    return line
 
 
 def main():
