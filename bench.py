@@ -403,15 +403,15 @@ def gpu_run(args, cfg):
         nY = hY.numpy() if hY is not None else None
         nX = hX.numpy() if hX is not None else None
         h2d = (nY.nbytes if nY is not None else 0) + (nX.nbytes if nX is not None else 0)
-        init_A = np.copy(gem.init_A)
         d2h_box = [0]
 
         def e2e_step():
             flush.zero_()
             # what a user of the reference does per fit: build the model from the host
-            # count matrices (this rank's rows, float64 as np.loadtxt returns them), run
-            # the EM iteration, read every output gem2csv writes back to the host
-            g2 = make_gem(SCexpr=nY, BKexpr=nX, init_A=init_A, local_rows=True,
+            # count matrices (this rank's rows, float64 as np.loadtxt returns them; the
+            # parameters are initialised from them, gem.py:208-280), run the EM iteration,
+            # read every output gem2csv writes back to the host
+            g2 = make_gem(SCexpr=nY, BKexpr=nX, local_rows=True,
                           L_total=Ll * world, M_total=Ml * world,
                           row_offset_SC=rank * Ll, row_offset_BK=rank * Ml)
             g2.init_gibbs()

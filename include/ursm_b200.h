@@ -153,6 +153,14 @@ int ursm_bk_kernel_ms(ursm_bk* bk, float* ms);
  * ursm_mle_closed_form  the bulk-only column rule :149-153
  * ursm_mle_elbo_terms   the A-dependent sums of compute_elbo :290-320
  */
+/* ---- parameter initialisation: gem.py:225-255 with utils.std_row utils.py:34-38 -------------
+ * ursm_sc_type_sums    d_out[k][i] = sum over this shard's cells of type k of Y_li / sum_i Y_li
+ *                      (the caller all-reduces and divides by the global cell count of the type)
+ * ursm_bk_profile_sum  d_out[i]    = sum over this shard's bulk samples of X_ji / sum_i X_ji
+ * One streaming pass over the device-resident counts each (4 B per entry). */
+int ursm_sc_type_sums(ursm_sc* sc, double* d_out, void* stream);
+int ursm_bk_profile_sum(ursm_bk* bk, double* d_out, void* stream);
+
 int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t K, double min_A);
 int ursm_mle_destroy(ursm_mle* m);
 int ursm_mle_set_A(ursm_mle* m, const double* h_A);

@@ -50,6 +50,8 @@ SIGNATURES = {
     "ursm_bk_gibbs": (c_int, [c_vp, c_i32, c_i32, c_i32, c_u64, c_u64, c_i32, c_vp, c_vp]),
     "ursm_bk_get_sample_stats": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_bk_get_W": (c_int, [c_vp, c_vp]),
+    "ursm_sc_type_sums": (c_int, [c_vp, c_vp, c_vp]),
+    "ursm_bk_profile_sum": (c_int, [c_vp, c_vp, c_vp]),
     "ursm_mle_create": (c_int, [PP, c_vp, c_vp, c_i32, c_i32, c_dbl]),
     "ursm_mle_destroy": (c_int, [c_vp]),
     "ursm_mle_set_A": (c_int, [c_vp, c_vp]),

@@ -527,6 +527,20 @@ int ursm_bk_destroy(ursm_bk* bk) {
   URSM_API_END
 }
 
+int ursm_bk_profile_sum(ursm_bk* bk, double* d_out, void* stream) {
+  URSM_API_BEGIN
+  BkShard* b = reinterpret_cast<BkShard*>(bk);
+  URSM_REQUIRE(b && d_out, "ursm_bk_profile_sum: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<double> R;
+  R.alloc((size_t)b->M);
+  launch_rowsum(b->X, b->M, b->N, R.p, st);
+  URSM_CUDA(cudaMemsetAsync(d_out, 0, (size_t)b->N * sizeof(double), st));
+  launch_normalised_colsum(b->X, nullptr, nullptr, R.p, b->M, b->N, b->num_sms, d_out, st);
+  URSM_CUDA(cudaStreamSynchronize(st));  // R is released on the default stream
+  URSM_API_END
+}
+
 int64_t ursm_bk_stats_len(const ursm_bk* bk) {
   const BkShard* b = reinterpret_cast<const BkShard*>(bk);
   return (int64_t)b->N * b->K + b->K + 1;

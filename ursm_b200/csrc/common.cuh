@@ -97,6 +97,12 @@ struct DevBuf {  // owning device buffer
 
 // host fp64 matrix -> device fp32 (staged through the device in chunks, cast there; sc_gibbs.cu)
 void upload_f64_as_f32(const double* h, float* d, size_t n);
+// row sums of an fp32 [L][N] matrix; and out[type][i] += sum_{rows of the type} Y[row][i] / R[row]
+// (type-sorted `order` and `G`, or both null: one type, natural order) -- the per-type means of
+// the row-normalised counts that parameter initialisation needs (gem.py:225-255); sc_gibbs.cu
+void launch_rowsum(const float* Y, long long L, int N, double* R, cudaStream_t st);
+void launch_normalised_colsum(const float* Y, const int* order, const int* G, const double* R,
+                              long long L, int N, int num_sms, double* out, cudaStream_t st);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ double warp_sum(double v) {

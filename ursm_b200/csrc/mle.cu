@@ -28,7 +28,7 @@ struct Mle {
   BkShard* bk = nullptr;
   int N = 0, K = 0;
   double min_A = 1e-6;
-  DevBuf<double> A, Anew, y, grad;       // [K][N]
+  DevBuf<double> A, y;                   // [K][N] columns; scratch of the closed-form rule
   const double* cAinv = nullptr;         // [K][N] caller-owned (all-reduced)
   const double* cA = nullptr;
   const double* coeffA = nullptr;
@@ -641,9 +641,7 @@ int ursm_mle_create(ursm_mle** out, ursm_sc* sc, ursm_bk* bk, int32_t N, int32_t
     m->num_sms = device_sm_count();
     const size_t KN = (size_t)K * N;
     m->A.alloc(KN);
-    m->Anew.alloc(KN);
     m->y.alloc(KN);
-    m->grad.alloc(KN);
     m->act_cur.alloc(K);
     m->act_next.alloc(K);
     m->niter.alloc(K);

@@ -503,6 +503,60 @@ __global__ void cast_f64_f32_kernel(const double* in, float* out, size_t n) {
   for (; i < n; i += stride) out[i] = (float)in[i];
 }
 
+// out[type][i] += sum over the chunk's rows of Y[row][i] / R[row]: one streaming pass over
+// the counts (4 B per entry), a thread owns four adjacent genes (16-byte loads), four rows
+// in flight, per-type partials flushed with fp64 atomics (std_row + the per-type means of
+// gem.py:225-255, utils.py:34-38; a read-less row gives NaN as it does there).
+__global__ void __launch_bounds__(256)
+normalised_colsum_kernel(const float* Y, const int* order, const int* G, const double* R,
+                         long long L, int N, int chunk, double* out) {
+  const int i = 4 * (blockIdx.x * 256 + threadIdx.x);
+  if (i >= N) return;
+  const long long c0 = (long long)blockIdx.y * chunk, c1 = min(L, c0 + (long long)chunk);
+  const bool vec = (i + 3 < N) && ((N & 3) == 0);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  int cur = -1;
+  for (long long c = c0; c < c1; c += 4) {
+    float4 v[4];
+    double w[4];
+    int ty[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool ok = c + q < c1;
+      const long long l = ok ? (order ? (long long)order[c + q] : c + q) : 0;
+      ty[q] = ok ? (G ? G[l] : 0) : -1;
+      w[q] = ok ? 1.0 / R[l] : 0.0;
+      const float* row = Y + (size_t)l * N + i;
+      if (!ok) {
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (vec) {
+        v[q] = *reinterpret_cast<const float4*>(row);
+      } else {
+        v[q] = make_float4(row[0], i + 1 < N ? row[1] : 0.f, i + 2 < N ? row[2] : 0.f,
+                           i + 3 < N ? row[3] : 0.f);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (ty[q] < 0) continue;
+      if (ty[q] != cur) {
+        if (cur >= 0)
+          for (int r = 0; r < 4; ++r)
+            if (i + r < N && acc[r] != 0.0) atomicAdd(&out[(size_t)cur * N + i + r], acc[r]);
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+        cur = ty[q];
+      }
+      acc[0] += (double)v[q].x * w[q];
+      acc[1] += (double)v[q].y * w[q];
+      acc[2] += (double)v[q].z * w[q];
+      acc[3] += (double)v[q].w * w[q];
+    }
+  }
+  if (cur >= 0)
+    for (int r = 0; r < 4; ++r)
+      if (i + r < N && !(acc[r] == 0.0)) atomicAdd(&out[(size_t)cur * N + i + r], acc[r]);
+}
+
 template <class CT>
 __global__ void cnt_to_f64_kernel(const CT* cnt, double* out, size_t n, double inv) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -513,6 +567,22 @@ __global__ void cnt_to_f64_kernel(const CT* cnt, double* out, size_t n, double i
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+void launch_rowsum(const float* Y, long long L, int N, double* R, cudaStream_t st) {
+  sc_rowsum_kernel<<<(unsigned)L, 256, 0, st>>>(Y, L, N, R);
+  URSM_LAUNCH_CHECK();
+}
+
+void launch_normalised_colsum(const float* Y, const int* order, const int* G, const double* R,
+                              long long L, int N, int num_sms, double* out, cudaStream_t st) {
+  const int gx = (N + 4 * 256 - 1) / (4 * 256);
+  long long ny = std::max<long long>(1, (8LL * num_sms + gx - 1) / gx);
+  ny = std::min<long long>(std::min<long long>(ny, L), 65535);
+  const int chunk = (int)((L + ny - 1) / ny);
+  ny = (L + chunk - 1) / chunk;
+  normalised_colsum_kernel<<<dim3(gx, (unsigned)ny), 256, 0, st>>>(Y, order, G, R, L, N, chunk, out);
+  URSM_LAUNCH_CHECK();
+}
+
 void upload_f64_as_f32(const double* h, float* d, size_t n) {
   // chunked: stage fp64 on the device, cast there
   const size_t chunk = (size_t)1 << 24;
@@ -582,7 +652,6 @@ static void sc_pick_geometry(ScShard* s) {
   }
   URSM_REQUIRE(best > 0.0, "gene count too large for the chain-resident single-cell kernel "
                            "(10 bytes of shared memory per gene, at most 32 genes per thread)");
-  s->pad = 0;
   s->slots = s->T * s->g;
   long long want = (long long)s->num_sms * s->occ;
   s->grid = (int)std::max<long long>(1, std::min<long long>(want, s->L));
@@ -788,6 +857,16 @@ int ursm_sc_gibbs(ursm_sc* sc, int32_t burnin, int32_t sample, int32_t thin, uin
   s->sample = sample;
   s->cnt_ensure((sample <= 255 && !getenv("URSM_SC_CNT16")) ? 1 : 2);
   sc_launch(s, a, st);
+  URSM_API_END
+}
+
+int ursm_sc_type_sums(ursm_sc* sc, double* d_out, void* stream) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && d_out, "ursm_sc_type_sums: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  URSM_CUDA(cudaMemsetAsync(d_out, 0, (size_t)s->K * s->N * sizeof(double), st));
+  launch_normalised_colsum(s->Y, s->order.p, s->G.p, s->R.p, s->L, s->N, s->num_sms, d_out, st);
   URSM_API_END
 }
 

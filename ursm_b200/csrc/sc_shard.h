@@ -30,7 +30,6 @@ struct ScShard {
   DevBuf<double> A;              // [N][K] fp64 parameters (row-major, as given)
   DevBuf<float> Aslot;           // [K][slots] fp32 copy of A^T in the Gibbs kernel's slot order
   DevBuf<float> scratch;         // [grid][slots][2] CTA-private accumulators (L2-resident)
-  int pad = 0;                   // (unused: the slot layout is conflict free without padding)
   int T = 0, g = 0, slots = 0, smem = 0, occ = 0, grid = 0, num_sms = 0;
   bool acc_smem = false, has_params = false;
   double pkappa[2] = {0, 1}, ptau[2] = {0, 1};

@@ -64,18 +64,22 @@ class LogitNormalGibbs_SC(object):
     """Single-cell Gibbs sampler (e_step_gibbs.py:171-377)."""
 
     def __init__(self, A, pkappa, ptau, SCexpr, G, itype, row_offset=0, total_rows=None,
-                 seed=None, device_counts=None):
+                 seed=None, device_counts=None, K=None):
+        """`A=None` (with `K`) builds the device shard before any parameters exist -- the
+        driver does that to initialise the parameters from the device-resident counts --
+        and `update_parameters` installs them later."""
         torch = _lib.require_cuda()
         self._torch = torch
         (self.SCexpr, self.G) = (SCexpr, G)
-        self.L = int(SCexpr.shape[0] if SCexpr is not None else device_counts.shape[0])
-        (self.N, self.K) = A.shape
+        data = SCexpr if SCexpr is not None else device_counts
+        self.L = int(data.shape[0])
+        (self.N, self.K) = A.shape if A is not None else (int(data.shape[1]), int(K))
         self.itype = itype
         self.row_offset = int(row_offset)
         self.total_rows = int(total_rows) if total_rows is not None else self.L
-        self.A = np.array(A, dtype=float, copy=True)
-        self.pkappa = np.array(pkappa, dtype=float, copy=True)
-        self.ptau = np.array(ptau, dtype=float, copy=True)
+        self.A = np.array(A, dtype=float, copy=True) if A is not None else None
+        self.pkappa = np.array(pkappa, dtype=float, copy=True) if pkappa is not None else None
+        self.ptau = np.array(ptau, dtype=float, copy=True) if ptau is not None else None
         self.seed = _DEFAULT_SEED if seed is None else int(seed)
         self.em_iter = 0
         Gi = _lib.i64(np.asarray(G).ravel())
@@ -91,8 +95,16 @@ class LogitNormalGibbs_SC(object):
         self._h = h
         n = _lib.load().ursm_sc_stats_len(h)
         self._stats = torch.zeros(n, dtype=torch.float64, device="cuda")
-        self._push_params()
+        if self.A is not None:
+            self._push_params()
         self.suff_stats = {}
+
+    def type_sums(self):
+        """K x N: per type, the sum over this shard's cells of the row-normalised counts
+        (`std_row`, utils.py:34-38; the numerator of gem.py:234-238), one pass on the device."""
+        out = self._torch.empty(self.K * self.N, dtype=self._torch.float64, device="cuda")
+        _lib.call("ursm_sc_type_sums", self._h, ctypes.c_void_p(out.data_ptr()), _lib.stream_ptr())
+        return out.cpu().numpy().reshape(self.K, self.N)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -192,16 +204,18 @@ class LogitNormalGibbs_BK(object):
     """Bulk-sample Gibbs sampler / mean-update (e_step_gibbs.py:19-164)."""
 
     def __init__(self, A, alpha, BKexpr, iMarkers=None, row_offset=0, total_rows=None,
-                 seed=None, device_counts=None):
+                 seed=None, device_counts=None, K=None):
+        """`A=None` (with `K`): see LogitNormalGibbs_SC."""
         torch = _lib.require_cuda()
         self._torch = torch
         self.BKexpr, self.iMarkers = BKexpr, iMarkers
-        self.M = int(BKexpr.shape[0] if BKexpr is not None else device_counts.shape[0])
-        (self.N, self.K) = (A.shape[0], A.shape[1])
+        data = BKexpr if BKexpr is not None else device_counts
+        self.M = int(data.shape[0])
+        (self.N, self.K) = A.shape if A is not None else (int(data.shape[1]), int(K))
         self.row_offset = int(row_offset)
         self.total_rows = int(total_rows) if total_rows is not None else self.M
-        self.A = np.array(A, dtype=float, copy=True)
-        self.alpha = np.array(alpha, dtype=float, copy=True)
+        self.A = np.array(A, dtype=float, copy=True) if A is not None else None
+        self.alpha = np.array(alpha, dtype=float, copy=True) if alpha is not None else None
         self.seed = _DEFAULT_SEED if seed is None else int(seed)
         self.em_iter = 0
         self.freeze = 0  # parity hook: bit0 keep W, bit1 keep sum_i Z
@@ -217,8 +231,17 @@ class LogitNormalGibbs_BK(object):
         self._h = h
         n = _lib.load().ursm_bk_stats_len(h)
         self._stats = torch.zeros(n, dtype=torch.float64, device="cuda")
-        self._push_params()
+        if self.A is not None:
+            self._push_params()
         self.suff_stats = {}
+
+    def profile_sum(self):
+        """N-vector: the sum over this shard's bulk samples of the row-normalised counts
+        (the numerator of gem.py:228-230 / :246), one pass on the device."""
+        out = self._torch.empty(self.N, dtype=self._torch.float64, device="cuda")
+        _lib.call("ursm_bk_profile_sum", self._h, ctypes.c_void_p(out.data_ptr()),
+                  _lib.stream_ptr())
+        return out.cpu().numpy()
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None

@@ -25,7 +25,7 @@ import numpy as np
 from . import dist
 from .e_step_gibbs import LogitNormalGibbs_BK, LogitNormalGibbs_SC
 from .m_step import LogitNormalMLE
-from .utils import simplex_proj, std_row
+from .utils import simplex_proj
 
 
 class LogitNormalGEM(object):
@@ -94,6 +94,20 @@ class LogitNormalGEM(object):
         else:
             self.BKexpr = None
 
+        # the device shards exist from here on: the counts are uploaded once, parameter
+        # initialisation (below) and the samplers (init_gibbs) work on the same copy
+        self._shard_SC = self._shard_BK = None
+        if self.hasSC and self.L_local > 0:
+            self._shard_SC = LogitNormalGibbs_SC(
+                A=None, pkappa=None, ptau=None, SCexpr=self.SCexpr, G=self.G, itype=self.itype,
+                row_offset=self._off_SC, total_rows=self.L, seed=self.seed,
+                device_counts=self._dev_SC, K=self.K)
+        if self.hasBK and self.M_local > 0:
+            self._shard_BK = LogitNormalGibbs_BK(
+                A=None, alpha=None, BKexpr=self.BKexpr, iMarkers=self.iMarkers,
+                row_offset=self._off_BK, total_rows=self.M, seed=self.seed,
+                device_counts=self._dev_BK, K=self.K)
+
         self.init_para(init_A, init_pkappa, init_ptau, init_alpha)
 
     # ------------------------------------------------------------------
@@ -113,42 +127,18 @@ class LogitNormalGEM(object):
         self.init_para_A(init_A)
 
     def _type_means_SC(self):
-        """K x N per-type SUMS of row-normalised single-cell counts, over all ranks."""
-        K, N = self.K, self.N
-        sums = np.zeros((K, N))
-        if self._dev_SC is not None:
-            import torch as th
-            Y = self._dev_SC
-            acc = th.zeros(K, N, dtype=th.float64, device=Y.device)
-            Gd = th.as_tensor(self.G, device=Y.device)
-            step = max(1, (1 << 26) // N)
-            for r0 in range(0, Y.shape[0], step):
-                blk = Y[r0:r0 + step].double()
-                blk = blk / blk.sum(dim=1, keepdim=True)
-                acc.index_add_(0, Gd[r0:r0 + step], blk)
-            sums = acc.cpu().numpy()
-        elif self.L_local > 0:
-            stdY = std_row(np.asarray(self.SCexpr, dtype=float))
-            for k in range(K):
-                if len(self.itype[k]) > 0:
-                    sums[k] = stdY[self.itype[k], :].sum(axis=0)
+        """K x N per-type SUMS of row-normalised single-cell counts, over all ranks
+        (csrc: normalised_colsum_kernel, one pass over the device-resident counts)."""
+        sums = np.zeros((self.K, self.N))
+        if self._shard_SC is not None:
+            sums = self._shard_SC.type_sums()
         return dist.all_reduce_np(sums)
 
     def _mean_BK(self):
         """N-vector mean over ALL bulk samples of the row-normalised counts."""
-        if self._dev_BK is not None:
-            import torch as th
-            X = self._dev_BK
-            acc = th.zeros(self.N, dtype=th.float64, device=X.device)
-            step = max(1, (1 << 26) // self.N)
-            for r0 in range(0, X.shape[0], step):
-                blk = X[r0:r0 + step].double()
-                acc += (blk / blk.sum(dim=1, keepdim=True)).sum(dim=0)
-            s = acc.cpu().numpy()
-        elif self.M_local > 0:
-            s = std_row(np.asarray(self.BKexpr, dtype=float)).sum(axis=0)
-        else:
-            s = np.zeros(self.N)
+        s = np.zeros(self.N)
+        if self._shard_BK is not None:
+            s = self._shard_BK.profile_sum()
         return dist.all_reduce_np(s) / float(self.M)
 
     def init_para_A(self, init_A):
@@ -200,17 +190,16 @@ class LogitNormalGEM(object):
     # ------------------------------------------------------------------
     def init_gibbs(self):
         if self.hasSC:
-            self.Gibbs_SC = LogitNormalGibbs_SC(
-                A=self.init_A, pkappa=self.init_pkappa, ptau=self.init_ptau,
-                SCexpr=self.SCexpr, G=self.G, itype=self.itype,
-                row_offset=self._off_SC, total_rows=self.L, seed=self.seed,
-                device_counts=self._dev_SC)
+            if self._shard_SC is None:
+                raise ValueError("this rank holds no single cells")
+            self.Gibbs_SC = self._shard_SC
+            self.Gibbs_SC.update_parameters(self.init_A, self.init_pkappa, self.init_ptau)
             self.Gibbs_SC.init_gibbs()
         if self.hasBK:
-            self.Gibbs_BK = LogitNormalGibbs_BK(
-                A=self.init_A, alpha=self.init_alpha, BKexpr=self.BKexpr,
-                iMarkers=self.iMarkers, row_offset=self._off_BK, total_rows=self.M,
-                seed=self.seed, device_counts=self._dev_BK)
+            if self._shard_BK is None:
+                raise ValueError("this rank holds no bulk samples")
+            self.Gibbs_BK = self._shard_BK
+            self.Gibbs_BK.update_parameters(self.init_A, self.init_alpha)
             self.Gibbs_BK.init_gibbs()
 
     def init_mle(self):
