@@ -377,3 +377,29 @@ def test_counter_width_does_not_change_results(ub, N, monkeypatch):
     for a, b in zip(res[1][1:5], res[2][1:5]):
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(res[1][5], res[2][5], rtol=1e-6, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# parameter initialisation on the device (gem.py:225-255, utils.std_row utils.py:34-38)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [64, 203])
+def test_init_A_on_device_matches_reference_rule(ub, N):
+    K, L, M = 4, 53, 9
+    rs = np.random.RandomState(13)
+    sim = orc.simulate(N=N, K=K, L=L, M=M, seed=3, G=rs.randint(0, 3, L))  # type 3 has no cells
+    Y, X, G = sim["Y"], sim["X"], sim["G"]
+    itype = _itype(G, K)
+    want = orc.init_A(Y, X, K, itype, 1e-6)
+    gem = ub.gm.LogitNormalGEM(BKexpr=X, SCexpr=Y, K=K, G=G, burnin=1, sample=1)
+    np.testing.assert_allclose(gem.init_A, want, rtol=1e-9, atol=1e-13)
+    # the same rows declared as this rank's own block (bench.py's end-to-end arm)
+    gem2 = ub.gm.LogitNormalGEM(BKexpr=X, SCexpr=Y, K=K, G=G, burnin=1, sample=1, local_rows=True,
+                                L_total=L, M_total=M, row_offset_SC=0, row_offset_BK=0)
+    np.testing.assert_allclose(gem2.init_A, want, rtol=1e-9, atol=1e-13)
+    # bulk only / single cells only
+    np.testing.assert_allclose(ub.gm.LogitNormalGEM(BKexpr=X, K=K).init_A,
+                               orc.init_A(None, X, K, None, 1e-6), rtol=1e-9, atol=1e-13)
+    G3 = G % 3
+    np.testing.assert_allclose(
+        ub.gm.LogitNormalGEM(SCexpr=Y, K=3, G=G3, burnin=1, sample=1).init_A,
+        orc.init_A(Y, None, 3, _itype(G3, 3), 1e-6), rtol=1e-9, atol=1e-13)
