@@ -65,7 +65,9 @@ int ursm_host_trim(void);
  *   sum_l E[kappa] | sum_l E[kappa^2] | sum_l E[tau] | sum_l E[tau^2]
  *   -- the vector a multi-GPU caller all-reduces.
  * ursm_sc_get_cell_moments  suff_stats exp_kappa/exp_tau/exp_kappasq/exp_tausq (:233-236)
- * ursm_sc_get_exp_S         suff_stats["exp_S"] (:232) rows [row0,row0+nrows) as float64
+ * ursm_sc_get_exp_S         suff_stats["exp_S"] (:232) rows [row0,row0+nrows) as float64 (on the
+ *                            device it is a count per entry, one byte when sample <= 255, two
+ *                            otherwise: exp_S * sample is an integer)
  * ursm_sc_inject            parity hook: one update_suffStats(sample) (:245-270) on a
  *                            caller-supplied state (w, S, kappa, tau) instead of a drawn one
  * ursm_sc_sweep_debug       parity hook: ONE gibbs_cycle of the production kernel from
@@ -141,7 +143,7 @@ int ursm_bk_kernel_ms(ursm_bk* bk, float* ms);
  * ursm_mle_opt_begin/step/pass/merge/poll   opt_A_u :128-154 for every column that has cells,
  *                        all columns at once and without a host round trip per iteration:
  *     begin  arms the per-column loop state of opt_Ak :157-182 (active flag, iteration count)
- *     step   backtracking :209-233 -- kCand = 16 trial step sizes init_step/2^c of every active
+ *     step   backtracking :209-233 -- up to 16 trial step sizes init_step/2^c of every active
  *            column are projected (simplex_proj, utils.py:8-31) and tested CONCURRENTLY, then
  *            the first passing one is committed: the step the reference's sequential halving
  *            loop accepts; get_grad_A :262-272, get_obj_A :275-287.  d_cconst_part is the
@@ -149,6 +151,7 @@ int ursm_bk_kernel_ms(ursm_bk* bk, float* ms);
  *     pass   opt_u :108-115 + update_gd_coeffConst :118-125 for the stepped columns -> d_part_local
  *            (the caller all-reduces it across ranks)
  *     merge  installs the reduced partials of the stepped columns, advances the loop state
+ *            (pass_p2p / merge_p2p below: the same with the cross-rank sum inside the kernel)
  *     poll   device -> host: which columns are still iterating, iteration / halving counts
  * ursm_mle_closed_form  the bulk-only column rule :149-153
  * ursm_mle_elbo_terms   the A-dependent sums of compute_elbo :290-320
