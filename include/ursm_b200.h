@@ -184,7 +184,7 @@ int ursm_mle_opt_merge(ursm_mle* m, const double* d_part_local, double* d_part, 
  * is ONE kernel that signals the peers, waits for them and installs the rank-ordered sum read
  * over NVLink.  Blocks and their peer mappings are cached per process by size (`out_cached`:
  * this rank already holds the mappings; when every rank says so `open` needs no handles).
- * ursm_mle_p2p_error reports a peer that never showed up (the kernel gives up after ~2 s
+ * ursm_mle_p2p_error reports a peer that never showed up (the kernel gives up after ~20 s
  * instead of hanging). */
 int ursm_mle_p2p_alloc(ursm_mle* m, void* out_handle64, int32_t* out_cached);
 int ursm_mle_p2p_disable(ursm_mle* m);
