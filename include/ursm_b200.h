@@ -62,7 +62,9 @@ int ursm_host_trim(void);
  *                        sweeps.  ONE fused persistent kernel; chain state stays on chip.
  *   d_stats (device, caller-owned, length ursm_sc_stats_len()) receives, already
  *   divided by `sample`:  coeffA[N*K] | coeffAsq[N*K] | exp_elbo_const |
- *   sum_l E[kappa] | sum_l E[kappa^2] | sum_l E[tau] | sum_l E[tau^2]
+ *   sum_l E[kappa] | sum_l E[kappa^2] | sum_l E[tau] | sum_l E[tau^2] | failure count
+ *   (failure count: (cell, sweep) pairs whose draw_S scan :326-342 did not reach its fixed
+ *   point -- 0 in a correct run; the Python mirror raises otherwise)
  *   -- the vector a multi-GPU caller all-reduces.
  * ursm_sc_get_cell_moments  suff_stats exp_kappa/exp_tau/exp_kappasq/exp_tausq (:233-236)
  * ursm_sc_get_exp_S         suff_stats["exp_S"] (:232) rows [row0,row0+nrows) as float64 (on the
@@ -94,6 +96,16 @@ int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kapp
                         const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t sweep,
                         float* h_w_out, uint8_t* h_S_out, double* h_kappa_out,
                         double* h_tau_out, int32_t* h_scan_rounds);
+/* parity hook for update_suffStats :245-270 as the PRODUCTION kernel folds it: burnin +
+ * sample*thin gibbs_cycles (:307-312) from a caller-supplied (S, kappa, tau) with the retention
+ * schedule of gibbs :299-304; returns the state after EVERY sweep -- h_w_out / h_S_out
+ * [nsweeps][L][N], h_kt_out [nsweeps][2][L] (kappa row, tau row) -- and what the kernel
+ * accumulated from it: h_stats (ursm_sc_stats_len doubles, layout of ursm_sc_gibbs),
+ * h_cnt [L][N] (retained sweeps with S = 1), h_cellmom [4][L] (E kappa, E tau, E kappa^2, E tau^2) */
+int ursm_sc_chain_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kappa_in,
+                        const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t burnin,
+                        int32_t sample, int32_t thin, float* h_w_out, uint8_t* h_S_out,
+                        double* h_kt_out, double* h_stats, uint16_t* h_cnt, double* h_cellmom);
 /* device time (ms, CUDA events on the launch stream) of the last Gibbs kernel */
 int ursm_sc_kernel_ms(ursm_sc* sc, float* ms);
 /* launch geometry the shard picked (threads per CTA, genes per thread, CTAs) */
@@ -185,8 +197,14 @@ int ursm_mle_opt_merge(ursm_mle* m, const double* d_part_local, double* d_part, 
  * over NVLink.  Blocks and their peer mappings are cached per process by size (`out_cached`:
  * this rank already holds the mappings; when every rank says so `open` needs no handles).
  * ursm_mle_p2p_error reports a peer that never showed up (the kernel gives up after ~20 s
- * instead of hanging). */
+ * instead of hanging).
+ * ursm_mle_p2p_state -> {usable cached mapping?, block id, epoch, peers mapped?}: every rank
+ * of a job must report the same first three before a cached block is reused without a handshake;
+ * ursm_mle_p2p_reset zeroes this rank's flag words, the error word and the epoch (the caller
+ * puts a barrier on both sides). */
 int ursm_mle_p2p_alloc(ursm_mle* m, void* out_handle64, int32_t* out_cached);
+int ursm_mle_p2p_state(ursm_mle* m, int64_t* out4);
+int ursm_mle_p2p_reset(ursm_mle* m);
 int ursm_mle_p2p_disable(ursm_mle* m);
 int ursm_mle_p2p_open(ursm_mle* m, const void* handles, int32_t world, int32_t rank);
 int ursm_mle_opt_pass_p2p(ursm_mle* m, void* stream);

@@ -26,13 +26,21 @@ if world > 1:
 from oracle import ursm_oracle as orc
 from ursm_b200.gem import LogitNormalGEM
 sim = orc.simulate(N=400, K=3, L=90, M=12, seed=5)
-gem = LogitNormalGEM(BKexpr=sim["X"], SCexpr=sim["Y"], K=3, G=sim["G"], burnin=10, sample=20,
-                     thin=1, bk_mean_approx=True, MLE_CONV=1e-6, MLE_maxiter=60, EM_CONV=1e-9,
-                     EM_maxiter=3, seed=9)
-niter, elbo, conv, path = gem.gem()
+def fit():
+    gem = LogitNormalGEM(BKexpr=sim["X"], SCexpr=sim["Y"], K=3, G=sim["G"], burnin=10, sample=20,
+                         thin=1, bk_mean_approx=True, MLE_CONV=1e-6, MLE_maxiter=60, EM_CONV=1e-9,
+                         EM_maxiter=3, seed=9)
+    niter, elbo, conv, path = gem.gem()
+    return gem, path
+gem, path = fit()
+# a second fit in the same process: a NEW M-step workspace reuses the cached peer block
+# through the one-collective fast path (same block id and epoch on every rank)
+gem2, path2 = fit()
 if int(os.environ.get("RANK", "0")) == 0:
     print("RESULT " + json.dumps({"path": [float(x) for x in path], "A": gem.A.tolist(),
-                                  "p2p": bool(getattr(gem.mle, "_p2p", False))}))
+                                  "path2": [float(x) for x in path2],
+                                  "p2p": bool(getattr(gem.mle, "_p2p", False)),
+                                  "p2p2": bool(getattr(gem2.mle, "_p2p", False))}))
 if world > 1:
     td.destroy_process_group()
 """
@@ -62,7 +70,8 @@ def test_two_ranks_peer_exchange_matches_nccl_and_single_rank():
     one = _run(1, {})
     p2p = _run(2, {"URSM_MLE_P2P": "1"})
     nccl = _run(2, {"URSM_MLE_P2P": "0"})
-    assert p2p["p2p"] and not nccl["p2p"]
+    assert p2p["p2p"] and p2p["p2p2"] and not nccl["p2p"]
+    np.testing.assert_allclose(p2p["path2"], p2p["path"], rtol=2e-5)  # cached block, second fit
     # chains do not depend on the sharding; the statistics are summed in a different order
     for other in (p2p, nccl):
         np.testing.assert_allclose(other["path"], one["path"], rtol=2e-5)

@@ -347,7 +347,24 @@ def test_degenerate_sizes(ub):
 # chains and everything the M-step derives from the counters must not depend on it
 # (ragged N: the 8-byte vector loads fall back to the scalar path)
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("N", [96, 101])
+def test_counts_above_2p24_are_refused(ub):
+    """Counts are stored as fp32 on the device; the reference splits float64 counts exactly
+    (e_step_gibbs.py:137), so an entry fp32 cannot hold is an error, not a rounding."""
+    from ursm_b200 import _lib
+    X = np.full((3, 8), 5.0)
+    X[1, 2] = 2.0 ** 24 + 1
+    with pytest.raises(_lib.UrsmError, match="2\^24"):
+        ub.es.LogitNormalGibbs_BK(np.full((8, 2), 1.0 / 8), np.ones(2), X)
+    Y = np.full((3, 8), 1.0)
+    Y[0, 0] = -1.0
+    with pytest.raises(_lib.UrsmError, match="2\^24"):
+        ub.es.LogitNormalGibbs_SC(np.full((8, 2), 1.0 / 8), np.array([-1., .01]), np.array([8., .08]),
+                                  Y, np.array([0, 1, 0]), None)
+    X[1, 2] = 2.0 ** 24  # the largest exact count is fine
+    ub.es.LogitNormalGibbs_BK(np.full((8, 2), 1.0 / 8), np.ones(2), X)
+
+
+@pytest.mark.parametrize("N", [96, 101, 4801, 5000])
 def test_counter_width_does_not_change_results(ub, N, monkeypatch):
     K, L = 3, 40
     sim = orc.simulate(N=N, K=K, L=L, M=0, seed=11)

@@ -37,6 +37,8 @@ SIGNATURES = {
     "ursm_sc_inject": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ursm_sc_sweep_debug": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_u64, c_i32, c_vp, c_vp,
                                     c_vp, c_vp, c_vp]),
+    "ursm_sc_chain_debug": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_u64, c_i32, c_i32, c_i32,
+                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ursm_sc_kernel_ms": (c_int, [c_vp, c_vp]),
     "ursm_bk_kernel_ms": (c_int, [c_vp, c_vp]),
     "ursm_sc_geometry": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -65,6 +67,8 @@ SIGNATURES = {
     "ursm_mle_opt_merge": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_opt_poll": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_p2p_alloc": (c_int, [c_vp, c_vp, c_vp]),
+    "ursm_mle_p2p_state": (c_int, [c_vp, c_vp]),
+    "ursm_mle_p2p_reset": (c_int, [c_vp]),
     "ursm_mle_p2p_disable": (c_int, [c_vp]),
     "ursm_mle_p2p_open": (c_int, [c_vp, c_vp, c_i32, c_i32]),
     "ursm_mle_opt_pass_p2p": (c_int, [c_vp, c_vp]),

@@ -60,7 +60,9 @@ struct P2PBlock {
   int world = 0, rank = 0;
   unsigned long long epoch = 0;
   int* err = nullptr;
+  int id = 0;           // index in g_p2p_blocks: the ranks of a job must agree on it
   bool opened = false, in_use = false;
+  bool dirty = false;   // a barrier timed out on this block: flags / epoch must be reset
 };
 static std::vector<P2PBlock*> g_p2p_blocks;
 
@@ -837,6 +839,8 @@ int ursm_mle_opt_step(ursm_mle* mm, const double* d_cconst_part, void* stream) {
   const int T = std::max(64, std::min(1024, (m->N / 4 + 31) / 32 * 32));
   const size_t ybytes = (size_t)m->N * sizeof(double);
   a.y_smem = ybytes <= (size_t)160 * 1024 ? 1 : 0;
+  if (const char* e = getenv("URSM_MLE_Y_SMEM"))  // tests: the global-memory trial column
+    a.y_smem = (a.y_smem && atoi(e)) ? 1 : 0;
   const size_t dyn = a.y_smem ? ybytes : 0;
   static size_t configured = 0;
   if (dyn > 48 * 1024 && dyn > configured) {
@@ -905,12 +909,13 @@ int ursm_mle_p2p_alloc(ursm_mle* mm, void* out_handle64, int32_t* out_cached) {
       URSM_CUDA(cudaMalloc((void**)&b->err, sizeof(int)));
       URSM_CUDA(cudaMemset(b->err, 0, sizeof(int)));
       URSM_CUDA(cudaDeviceSynchronize());
+      b->id = (int)g_p2p_blocks.size();
       g_p2p_blocks.push_back(b);
       m->p2p = b;
     }
     m->p2p->in_use = true;
   }
-  *out_cached = m->p2p->opened ? 1 : 0;
+  *out_cached = (m->p2p->opened && !m->p2p->dirty) ? 1 : 0;
   cudaIpcMemHandle_t h;
   URSM_CUDA(cudaIpcGetMemHandle(&h, m->p2p->own));
   memcpy(out_handle64, &h, sizeof h);
@@ -940,6 +945,31 @@ int ursm_mle_p2p_open(ursm_mle* mm, const void* handles, int32_t world, int32_t 
     b->rank = rank;
     b->opened = true;
   }
+  URSM_API_END
+}
+
+int ursm_mle_p2p_state(ursm_mle* mm, int64_t* out4) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && m->p2p && out4, "ursm_mle_p2p_state: call ursm_mle_p2p_alloc first");
+  out4[0] = (m->p2p->opened && !m->p2p->dirty) ? 1 : 0;
+  out4[1] = m->p2p->id;
+  out4[2] = (int64_t)m->p2p->epoch;
+  out4[3] = m->p2p->opened ? 1 : 0;
+  URSM_API_END
+}
+
+int ursm_mle_p2p_reset(ursm_mle* mm) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && m->p2p, "ursm_mle_p2p_reset: call ursm_mle_p2p_alloc first");
+  P2PBlock* b = m->p2p;
+  URSM_CUDA(cudaDeviceSynchronize());
+  URSM_CUDA(cudaMemset(p2p_flags(m, b->own), 0, kMaxPeers * sizeof(unsigned long long)));
+  URSM_CUDA(cudaMemset(b->err, 0, sizeof(int)));
+  URSM_CUDA(cudaDeviceSynchronize());
+  b->epoch = 0;
+  b->dirty = false;
   URSM_API_END
 }
 
@@ -991,8 +1021,10 @@ int ursm_mle_p2p_error(ursm_mle* mm, int32_t* h_err) {
   Mle* m = reinterpret_cast<Mle*>(mm);
   URSM_REQUIRE(m && h_err, "ursm_mle_p2p_error: bad argument");
   *h_err = 0;
-  if (m->p2p && m->p2p->err)
+  if (m->p2p && m->p2p->err) {
     URSM_CUDA(cudaMemcpy(h_err, m->p2p->err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*h_err) m->p2p->dirty = true;  // the next fit resets the block behind a barrier
+  }
   URSM_API_END
 }
 

@@ -58,7 +58,7 @@ struct ScGibbsArgs {
   void* cnt;            // [L][N] counters, cnt_w bytes each
   int cnt_w;
   double* cellmom;      // [4][L]
-  double* stats;        // coeffA[K][N] | coeffAsq[K][N] | elbo | sk | skk | st | stt
+  double* stats;        // coeffA[K][N] | coeffAsq[K][N] | elbo | sk | skk | st | stt | scan failures
   float* scratch;       // [grid][slots][2]
   int flush_every;
   int* counter;
@@ -70,6 +70,7 @@ struct ScGibbsArgs {
   unsigned char* S_out;     // [L][N]
   double* kt_out;           // [2][L]
   int* rounds_out;          // [L]
+  int dump_all;             // w_out / S_out / kt_out hold EVERY sweep ([nsweeps][...]), not the last
 };
 
 // acc[slot] += (dA, dQ).  Shared memory or an L1-cached scratch row: plain 8-byte
@@ -351,7 +352,11 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
         const double incoming = s_cur + pre + inc - delta;
         const bool viol = !(fabs(incoming - used_in) < (double)margin) && incoming != used_in &&
                           margin != INFINITY;
-        if (!__syncthreads_or(viol) || rounds > T) {
+        const bool more = __syncthreads_or(viol);
+        // stats tail slot 5 counts (cell, sweep) pairs whose scan hit the round limit: never
+        // seen, but the host raises if it ever is (it rides the statistics all-reduce)
+        if (more && rounds > T && tid == 0) atomicAdd(&scal[5], 1.0);
+        if (!more || rounds > T) {
           // ---- draw_kappa_tau (:345-377): warp 0 sums the per-warp partials, one thread
           // solves the 2x2 system and draws from the precomputed normal pair
           if (warp == 0) {
@@ -405,6 +410,20 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       prev_ret = retained;
       pk = (float)kappa;
       pt = (float)tau;
+      if (a.dump_all) {  // parity hook (ursm_sc_chain_debug): the state after EVERY sweep
+        const size_t sw_i = (size_t)(sweep - a.sweep0);
+        const size_t base = (sw_i * a.L + l) * N;
+        for (int i = tid; i < N; i += T) {
+          const int slot = slot_of_gene(i, g, T, inv_g);
+          a.w_out[base + i] = w_s[slot];
+          a.S_out[base + i] = (Sm_s[slot % T] >> (slot / T)) & 1u;
+        }
+        if (tid == 0) {
+          a.kt_out[sw_i * 2 * a.L + l] = kappa;
+          a.kt_out[sw_i * 2 * a.L + a.L + l] = tau;
+        }
+        __syncthreads();  // the next sweep overwrites w_s
+      }
     }
     // ---- fold of the last sweep (owner threads, own runs), write-back
     if (prev_ret) {
@@ -425,8 +444,8 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
         static_cast<unsigned char*>(a.cnt)[(size_t)l * N + i] = (unsigned char)cnt_s[slot];
       else
         static_cast<unsigned short*>(a.cnt)[(size_t)l * N + i] = cnt_s[slot];
-      if (a.w_out) a.w_out[(size_t)l * N + i] = w_s[slot];
-      if (a.S_out) {
+      if (a.w_out && !a.dump_all) a.w_out[(size_t)l * N + i] = w_s[slot];
+      if (a.S_out && !a.dump_all) {
         const int to = slot % T, j = slot / T;
         a.S_out[(size_t)l * N + i] = (Sm_s[to] >> j) & 1u;
       }
@@ -441,7 +460,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       atomicAdd(&scal[2], m_kk * inv_sample);
       atomicAdd(&scal[3], m_t * inv_sample);
       atomicAdd(&scal[4], m_tt * inv_sample);
-      if (a.kt_out) {
+      if (a.kt_out && !a.dump_all) {
         a.kt_out[l] = kappa;
         a.kt_out[a.L + l] = tau;
       }
@@ -497,10 +516,18 @@ __global__ void sc_rowsum_kernel(const float* Y, long long L, int N, double* R) 
   if (threadIdx.x == 0) R[l] = s;
 }
 
-__global__ void cast_f64_f32_kernel(const double* in, float* out, size_t n) {
+// fp64 -> fp32 storage of a count matrix; *bad is set when an entry is not a count that
+// fp32 holds exactly (negative, non-finite or above 2^24)
+__global__ void cast_f64_f32_kernel(const double* in, float* out, size_t n, int* bad) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) out[i] = (float)in[i];
+  bool b = false;
+  for (; i < n; i += stride) {
+    const double v = in[i];
+    b = b || !(v >= 0.0 && v <= 16777216.0);
+    out[i] = (float)v;
+  }
+  if (b) *bad = 1;
 }
 
 // out[type][i] += sum over the chunk's rows of Y[row][i] / R[row]: one streaming pass over
@@ -587,14 +614,22 @@ void upload_f64_as_f32(const double* h, float* d, size_t n) {
   // chunked: stage fp64 on the device, cast there
   const size_t chunk = (size_t)1 << 24;
   DevBuf<double> stage;
+  DevBuf<int> bad;
   stage.alloc(std::min(n, chunk));
+  bad.alloc(1);
+  bad.zero();
   for (size_t off = 0; off < n; off += chunk) {
     size_t m = std::min(chunk, n - off);
     URSM_CUDA(cudaMemcpy(stage.p, h + off, m * sizeof(double), cudaMemcpyHostToDevice));
-    cast_f64_f32_kernel<<<1184, 256>>>(stage.p, d + off, m);
+    cast_f64_f32_kernel<<<1184, 256>>>(stage.p, d + off, m, bad.p);
     URSM_LAUNCH_CHECK();
   }
-  URSM_CUDA(cudaDeviceSynchronize());
+  int h_bad = 0;
+  URSM_CUDA(cudaMemcpy(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+  // the reference keeps counts in float64 (e_step_gibbs.py:137 splits them exactly); here they
+  // are stored as fp32, exact up to 2^24 -- refuse anything else instead of rounding it
+  URSM_REQUIRE(!h_bad, "count matrix holds an entry that is negative, not finite or above 2^24 "
+                       "(counts are stored as fp32 on the device)");
 }
 
 // Shared memory of one CTA with T threads x g genes per thread: reductions / broadcast /
@@ -654,6 +689,8 @@ static void sc_pick_geometry(ScShard* s) {
                            "(10 bytes of shared memory per gene, at most 32 genes per thread)");
   s->slots = s->T * s->g;
   long long want = (long long)s->num_sms * s->occ;
+  if (const char* e = getenv("URSM_SC_GRID"))  // tests: many cells (and type changes) per CTA
+    want = std::max(1, atoi(e));
   s->grid = (int)std::max<long long>(1, std::min<long long>(want, s->L));
   if (!s->acc_smem) s->scratch.alloc((size_t)s->grid * 2 * s->slots);
 }
@@ -712,6 +749,8 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
   a.counter = s->counter.p;
   URSM_CUDA(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
   a.acc_red = (!s->acc_smem && s->smem > 128 * 1024) ? 1 : 0;
+  if (const char* e = getenv("URSM_SC_ACC_RED"))  // tests: the reduction path on small inputs
+    a.acc_red = (!s->acc_smem && atoi(e)) ? 1 : 0;
   if (!s->ev0) {
     URSM_CUDA(cudaEventCreate(&s->ev0));
     URSM_CUDA(cudaEventCreate(&s->ev1));
@@ -785,7 +824,7 @@ int ursm_sc_destroy(ursm_sc* sc) {
 
 int64_t ursm_sc_stats_len(const ursm_sc* sc) {
   const ScShard* s = reinterpret_cast<const ScShard*>(sc);
-  return 2 * (int64_t)s->N * s->K + 5;
+  return 2 * (int64_t)s->N * s->K + 6;
 }
 
 int ursm_sc_geometry(const ursm_sc* sc, int32_t* threads, int32_t* genes_per_thread, int32_t* grid,
@@ -946,26 +985,30 @@ int ursm_sc_inject(ursm_sc* sc, const double* h_w, const int64_t* h_S, const dou
   URSM_API_END
 }
 
-int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kappa_in,
-                        const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t sweep,
-                        float* h_w_out, uint8_t* h_S_out, double* h_kappa_out, double* h_tau_out,
-                        int32_t* h_scan_rounds) {
-  URSM_API_BEGIN
-  ScShard* s = reinterpret_cast<ScShard*>(sc);
-  URSM_REQUIRE(s && h_S_in && h_kappa_in && h_tau_in, "ursm_sc_sweep_debug: bad argument");
-  URSM_REQUIRE(s->has_params, "ursm_sc_sweep_debug: call ursm_sc_set_params first");
+// Parity hook: `nsweeps` production gibbs_cycles from a supplied (S, kappa, tau), starting at
+// sweep index `sweep0`, with the retention schedule (burnin, thin, sample) of ursm_sc_gibbs.
+// Returns the state after EVERY sweep and what the production update_suffStats fold made of
+// it: the packed statistics vector, the E[S] counters and the per-cell moments.
+static void sc_chain_debug(ScShard* s, const int64_t* h_S_in, const double* h_kappa_in,
+                           const double* h_tau_in, uint64_t seed, uint64_t em_iter, int sweep0,
+                           int nsweeps, int burnin, int thin, int sample, bool dump_all,
+                           float* h_w_out, uint8_t* h_S_out, double* h_kt_out,
+                           int32_t* h_scan_rounds, double* h_stats, uint16_t* h_cnt,
+                           double* h_cellmom) {
   const size_t LN = (size_t)s->L * s->N, L = s->L;
+  const size_t reps = dump_all ? (size_t)nsweeps : 1;
   DevBuf<unsigned char> S0, Sout;
   DevBuf<double> kt0, ktout, stats;
   DevBuf<float> wout;
   DevBuf<int> rounds;
   S0.alloc(LN);
-  Sout.alloc(LN);
-  wout.alloc(LN);
+  Sout.alloc(LN * reps);
+  wout.alloc(LN * reps);
   kt0.alloc(2 * L);
-  ktout.alloc(2 * L);
+  ktout.alloc(2 * L * reps);
   rounds.alloc(L);
-  stats.alloc((size_t)ursm_sc_stats_len(sc));
+  const size_t nstats = (size_t)(2 * (int64_t)s->N * s->K + 6);
+  stats.alloc(nstats);
   stats.zero();
   std::vector<unsigned char> S8(LN);
   for (size_t i = 0; i < LN; ++i) S8[i] = h_S_in[i] != 0;
@@ -974,11 +1017,11 @@ int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kapp
   URSM_CUDA(cudaMemcpy(kt0.p + L, h_tau_in, L * sizeof(double), cudaMemcpyHostToDevice));
   ScGibbsArgs a;
   memset(&a, 0, sizeof a);
-  a.burnin = sweep;  // the single sweep counts as retained
-  a.nsweeps = 1;
-  a.thin = 1;
-  a.sample = 1;
-  a.sweep0 = sweep;
+  a.burnin = burnin;
+  a.nsweeps = nsweeps;
+  a.thin = thin;
+  a.sample = sample;
+  a.sweep0 = sweep0;
   a.key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1);
   a.rk = philox_keys(a.key);
   a.stats = stats.p;
@@ -988,18 +1031,54 @@ int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kapp
   a.S_out = Sout.p;
   a.kt_out = ktout.p;
   a.rounds_out = rounds.p;
-  s->sample = 1;
+  a.dump_all = dump_all ? 1 : 0;
+  s->sample = sample;
   s->cnt_ensure(2);
   sc_launch(s, a, 0);
   URSM_CUDA(cudaDeviceSynchronize());
-  if (h_w_out) URSM_CUDA(cudaMemcpy(h_w_out, wout.p, LN * sizeof(float), cudaMemcpyDeviceToHost));
-  if (h_S_out) URSM_CUDA(cudaMemcpy(h_S_out, Sout.p, LN, cudaMemcpyDeviceToHost));
-  if (h_kappa_out)
-    URSM_CUDA(cudaMemcpy(h_kappa_out, ktout.p, L * sizeof(double), cudaMemcpyDeviceToHost));
-  if (h_tau_out)
-    URSM_CUDA(cudaMemcpy(h_tau_out, ktout.p + L, L * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h_w_out)
+    URSM_CUDA(cudaMemcpy(h_w_out, wout.p, LN * reps * sizeof(float), cudaMemcpyDeviceToHost));
+  if (h_S_out) URSM_CUDA(cudaMemcpy(h_S_out, Sout.p, LN * reps, cudaMemcpyDeviceToHost));
+  if (h_kt_out)
+    URSM_CUDA(cudaMemcpy(h_kt_out, ktout.p, 2 * L * reps * sizeof(double), cudaMemcpyDeviceToHost));
   if (h_scan_rounds)
     URSM_CUDA(cudaMemcpy(h_scan_rounds, rounds.p, L * sizeof(int), cudaMemcpyDeviceToHost));
+  if (h_stats)
+    URSM_CUDA(cudaMemcpy(h_stats, stats.p, nstats * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h_cnt) URSM_CUDA(cudaMemcpy(h_cnt, s->cnt.p, LN * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  if (h_cellmom)
+    URSM_CUDA(cudaMemcpy(h_cellmom, s->cellmom.p, 4 * L * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kappa_in,
+                        const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t sweep,
+                        float* h_w_out, uint8_t* h_S_out, double* h_kappa_out, double* h_tau_out,
+                        int32_t* h_scan_rounds) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && h_S_in && h_kappa_in && h_tau_in, "ursm_sc_sweep_debug: bad argument");
+  URSM_REQUIRE(s->has_params, "ursm_sc_sweep_debug: call ursm_sc_set_params first");
+  std::vector<double> kt(2 * (size_t)s->L);
+  // the single sweep counts as retained (burnin = sweep, sample = 1)
+  sc_chain_debug(s, h_S_in, h_kappa_in, h_tau_in, seed, em_iter, sweep, 1, sweep, 1, 1, false,
+                 h_w_out, h_S_out, kt.data(), h_scan_rounds, nullptr, nullptr, nullptr);
+  if (h_kappa_out) memcpy(h_kappa_out, kt.data(), s->L * sizeof(double));
+  if (h_tau_out) memcpy(h_tau_out, kt.data() + s->L, s->L * sizeof(double));
+  URSM_API_END
+}
+
+int ursm_sc_chain_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kappa_in,
+                        const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t burnin,
+                        int32_t sample, int32_t thin, float* h_w_out, uint8_t* h_S_out,
+                        double* h_kt_out, double* h_stats, uint16_t* h_cnt, double* h_cellmom) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && h_S_in && h_kappa_in && h_tau_in, "ursm_sc_chain_debug: bad argument");
+  URSM_REQUIRE(s->has_params, "ursm_sc_chain_debug: call ursm_sc_set_params first");
+  URSM_REQUIRE(burnin >= 0 && sample >= 1 && thin >= 1 && burnin + sample * thin <= 4096,
+               "ursm_sc_chain_debug: bad sweep counts");
+  sc_chain_debug(s, h_S_in, h_kappa_in, h_tau_in, seed, em_iter, 0, burnin + sample * thin, burnin,
+                 thin, sample, true, h_w_out, h_S_out, h_kt_out, nullptr, h_stats, h_cnt, h_cellmom);
   URSM_API_END
 }
 

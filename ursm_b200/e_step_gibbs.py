@@ -161,6 +161,25 @@ class LogitNormalGibbs_SC(object):
                   _lib.ptr(rounds))
         return w, S_out, k_out, t_out, rounds
 
+    def chain_debug(self, S, kappa, tau, burnin, sample, thin=1, seed=None, em_iter=0):
+        """`burnin + sample*thin` production cycles from a supplied (S, kappa, tau).  Returns a
+        dict: per-sweep `w` [T, L, N], `S` [T, L, N], `kappa` / `tau` [T, L], and what the
+        production fold accumulated: `stats` (packed vector), `cnt` [L, N], `cellmom` [4, L]."""
+        S = _lib.i64(S)
+        kappa, tau = _lib.f64(np.ravel(kappa)), _lib.f64(np.ravel(tau))
+        T = int(burnin) + int(sample) * int(thin)
+        w = np.empty((T, self.L, self.N), dtype=np.float32)
+        S_out = np.empty((T, self.L, self.N), dtype=np.uint8)
+        kt = np.empty((T, 2, self.L))
+        stats = np.empty(2 * self.N * self.K + 6)
+        cnt = np.empty((self.L, self.N), dtype=np.uint16)
+        mom = np.empty((4, self.L))
+        _lib.call("ursm_sc_chain_debug", self._h, _lib.ptr(S), _lib.ptr(kappa), _lib.ptr(tau),
+                  ctypes.c_uint64(self.seed if seed is None else seed), ctypes.c_uint64(em_iter),
+                  int(burnin), int(sample), int(thin), _lib.ptr(w), _lib.ptr(S_out), _lib.ptr(kt),
+                  _lib.ptr(stats), _lib.ptr(cnt), _lib.ptr(mom))
+        return dict(w=w, S=S_out, kappa=kt[:, 0], tau=kt[:, 1], stats=stats, cnt=cnt, cellmom=mom)
+
     def kernel_ms(self):
         """Device time of the last Gibbs kernel (CUDA events on its launch stream)."""
         ms = ctypes.c_float()
@@ -194,6 +213,9 @@ class LogitNormalGibbs_SC(object):
         st["coeffA"] = np.ascontiguousarray(host[:N * K].reshape(K, N).T)
         st["coeffAsq"] = np.ascontiguousarray(host[N * K:2 * N * K].reshape(K, N).T)
         st["exp_elbo_const"] = float(host[2 * N * K])
+        if host[2 * N * K + 5] != 0:
+            raise _lib.UrsmError("single-cell Gibbs kernel: the draw_S scan did not reach its "
+                                 "fixed point for %d (cell, sweep) pairs" % int(host[2 * N * K + 5]))
         # hidden hand-over to LogitNormalMLE: device buffers + global scalar sums
         st["_ursm_sc"] = self
         st["_ursm_sc_sums"] = host[2 * N * K + 1:2 * N * K + 5].copy()  # sum k, k^2, t, t^2

@@ -84,7 +84,15 @@ class LogitNormalMLE(object):
     def _setup_p2p(self):
         """Peer-memory exchange for the per-iteration sum of opt_Ak (one NVLink domain, NCCL
         backend): every rank shares one IPC block, the handles travel once through
-        torch.distributed.  `URSM_MLE_P2P=0` keeps the NCCL all-reduce (A/B measurements)."""
+        torch.distributed.  `URSM_MLE_P2P=0` keeps the NCCL all-reduce (A/B measurements).
+
+        Blocks are cached per process (the reference's API builds a new M-step object per
+        fit).  A cached block is reused only when ONE small all-reduce shows that every rank
+        holds a usable mapping of the same block at the same epoch; anything else (first
+        use, a rank that picked another block, a fit that was aborted half way, a barrier
+        that timed out) goes through the full handshake: handles exchanged, flag words /
+        error word / epoch reset between two barriers -- or, if the ranks' cached mappings
+        cannot be trusted, the NCCL path for this fit."""
         import os
         import torch
         import torch.distributed as td
@@ -95,35 +103,52 @@ class LogitNormalMLE(object):
             return False
         handle = (ctypes.c_char * 64)()
         cached = ctypes.c_int32(0)
+        state = np.array([-1, -1, -1, 0], dtype=np.int64)  # usable, block id, epoch, opened
         ok = 1
         try:
             _lib.call("ursm_mle_p2p_alloc", self._h, ctypes.cast(handle, ctypes.c_void_p),
                       ctypes.byref(cached))
+            _lib.call("ursm_mle_p2p_state", self._h, _lib.ptr(state))
         except _lib.UrsmError as e:  # pragma: no cover
             logging.warning("peer-memory exchange unavailable (%s); using NCCL", e)
             ok = 0
-        # (ok, this rank already maps its peers, IPC handle) of every rank
+            state[:] = (-1, -1 - dist.rank(), -1, 0)  # cannot agree with anybody
+        # ---- fast path: one collective tells whether all ranks agree on (usable, id, epoch)
+        probe = torch.tensor([state[0], -state[0], state[1], -state[1], state[2], -state[2]],
+                             dtype=torch.int64, device="cuda")
+        td.all_reduce(probe, op=td.ReduceOp.MAX)
+        v = [int(x) for x in probe.tolist()]
+        agree = v[0] == -v[1] and v[2] == -v[3] and v[4] == -v[5]
+        if agree and v[0] == 1:
+            _lib.call("ursm_mle_p2p_open", self._h, None, world, dist.rank())
+            return True
+        # ---- slow path: first use, or the ranks' cached state differs
         gathered = [None] * world
-        td.all_gather_object(gathered, (ok, int(cached.value), bytes(handle.raw)))
-        if not all(g[0] for g in gathered):
-            _lib.call("ursm_mle_p2p_disable", self._h)
+        td.all_gather_object(gathered, (ok, int(state[3]), int(state[1]), bytes(handle.raw)))
+        n_opened = sum(g[1] for g in gathered)
+        if not all(g[0] for g in gathered) or len(set(g[2] for g in gathered)) != 1 \
+                or n_opened not in (0, world):
+            # a rank cannot take part, or the ranks hold different blocks / only some of them
+            # hold mappings: do not guess, this fit sums through NCCL
+            if ok:
+                _lib.call("ursm_mle_p2p_disable", self._h)
             return False
-        n_cached = sum(g[1] for g in gathered)
-        if n_cached not in (0, world):  # ranks disagree about the cache: do not guess
-            _lib.call("ursm_mle_p2p_disable", self._h)
-            return False
-        blob = b"".join(g[2] for g in gathered)
+        blob = b"".join(g[3] for g in gathered)
         try:
-            _lib.call("ursm_mle_p2p_open", self._h, ctypes.c_char_p(blob), world, dist.rank())
+            _lib.call("ursm_mle_p2p_open", self._h, None if n_opened else ctypes.c_char_p(blob),
+                      world, dist.rank())
             ok = 1
         except _lib.UrsmError as e:  # pragma: no cover
             logging.warning("peer-memory exchange unavailable (%s); using NCCL", e)
             ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-        td.all_reduce(flag, op=td.ReduceOp.MIN)  # all ranks or none
+        td.all_reduce(flag, op=td.ReduceOp.MIN)  # all ranks or none; also barrier #1
         if not int(flag.item()):
             _lib.call("ursm_mle_p2p_disable", self._h)
             return False
+        _lib.call("ursm_mle_p2p_reset", self._h)  # zero my flag words / error word / epoch
+        td.all_reduce(flag, op=td.ReduceOp.MIN)   # barrier #2: nobody signals before all reset
+        flag.item()
         return True
 
     @staticmethod
