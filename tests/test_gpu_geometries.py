@@ -197,7 +197,8 @@ def _replay_case(hostlib, Y, G, A, pk, pt, K, seed, sweeps):
         for l in range(L):
             a = A[:, G[l]].astype(np.float32).astype(np.float64)
             sum_AS = float((a * S_new[l]).sum())
-            m, cov = orc.sc_kappa_tau_posterior(w[l].astype(np.float64), S_new[l], a, sum_AS, N, pk, pt)
+            m, cov = orc.sc_kappa_tau_posterior(w[l].astype(np.float64), S_new[l].astype(np.int64), a,
+                                                sum_AS, N, pk, pt)
             hostlib.h_cell_normals(ctypes.c_uint64(key), l, sweep, nn)
             ch = np.linalg.cholesky(np.asarray(cov))
             want = np.asarray(m) + ch.dot(np.array([nn[0], nn[1]]))

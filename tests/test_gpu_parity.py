@@ -353,11 +353,11 @@ def test_counts_above_2p24_are_refused(ub):
     from ursm_b200 import _lib
     X = np.full((3, 8), 5.0)
     X[1, 2] = 2.0 ** 24 + 1
-    with pytest.raises(_lib.UrsmError, match="2\^24"):
+    with pytest.raises(_lib.UrsmError, match=r"2\^24"):
         ub.es.LogitNormalGibbs_BK(np.full((8, 2), 1.0 / 8), np.ones(2), X)
     Y = np.full((3, 8), 1.0)
     Y[0, 0] = -1.0
-    with pytest.raises(_lib.UrsmError, match="2\^24"):
+    with pytest.raises(_lib.UrsmError, match=r"2\^24"):
         ub.es.LogitNormalGibbs_SC(np.full((8, 2), 1.0 / 8), np.array([-1., .01]), np.array([8., .08]),
                                   Y, np.array([0, 1, 0]), None)
     X[1, 2] = 2.0 ** 24  # the largest exact count is fine
