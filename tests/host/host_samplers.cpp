@@ -29,10 +29,26 @@ void h_binomial(int n, double p, int count, uint64_t seed, int* out) {
   }
 }
 void h_binomial_f32(int n, double p, int count, uint64_t seed, int* out) {
+  static double lf2[URSM_BINOM_TABLE];
+  static bool ready = false;
+  if (!ready) {
+    binom_fill_table(lf2);
+    ready = true;
+  }
   for (int i = 0; i < count; ++i) {
     Philox g(seed, (uint32_t)i, 5u, 0u);
-    out[i] = binomial_f32(n, (float)p, (float)(1.0 - p), g);
+    out[i] = binomial_f32(n, (float)p, (float)(1.0 - p), g, lf2);
   }
+}
+// how many uniforms out of `count` fall beyond the fp32 mass sum (-1 returns) for Bin(n, r)
+int h_binom_mode_misses(int n, double r, int count, uint64_t seed) {
+  static double lf2[URSM_BINOM_TABLE];
+  binom_fill_table(lf2);
+  Philox g(seed, 0u, 6u, 0u);
+  int miss = 0;
+  for (int i = 0; i < count; ++i)
+    if (binom_mode_try(n, (float)r, (float)(1.0 - r), g.uniform(), lf2) < 0) ++miss;
+  return miss;
 }
 void h_gamma(double shape, int count, uint64_t seed, double* out) {
   for (int i = 0; i < count; ++i) {

@@ -372,6 +372,17 @@ URSM_HD int binomial(int n, double p, RNG& rng) {
 // `p` and its complement are passed separately (both are ratios of positive sums in
 // the caller), so 1 - p is never formed by subtraction.
 // ---------------------------------------------------------------------------
+#define URSM_BINOM_TABLE 1024
+#define URSM_BINOM_MODE_MAX 32.0f
+
+#if defined(__CUDA_ARCH__)
+#define URSM_LG2(x) ::ursm::mufu_lg2(x)
+#define URSM_EX2(x) ::ursm::mufu_ex2(x)
+#else
+#define URSM_LG2(x) log2f(x)
+#define URSM_EX2(x) exp2f(x)
+#endif
+
 enum : int { kBinDone = 0, kBinInv = 1, kBinBtrs = 2, kBinRetry = 3 };
 
 struct BinomState {
@@ -464,8 +475,9 @@ URSM_HD float btrs_fc(int k) {  // Stirling series tail: log(k!) - Stirling's fo
   return (1.0f / 12 - (1.0f / 360 - 1.0f / 1260 * ik2) * ik2) * ik;
 }
 
-// one BTRS attempt from two uniforms; kBinDone on acceptance
-URSM_HD void binom_btrs_attempt(BinomState& b, float U, float V) {
+// one BTRS attempt from two uniforms; kBinDone on acceptance.  `lf2` (log2 k! table, may be
+// null) makes the exact test O(1) for n inside the table.
+URSM_HD void binom_btrs_attempt(BinomState& b, float U, float V, const double* lf2 = nullptr) {
   const float n = (float)b.n, r = b.r;
   const float spq = sqrtf(n * r * b.rc);
   const float bb = 1.15f + 2.53f * spq;
@@ -484,7 +496,12 @@ URSM_HD void binom_btrs_attempt(BinomState& b, float U, float V) {
     const float lhs = URSM_DIV(V * alpha, URSM_DIV(aa, us * us) + bb);
     const int m = (int)floorf((n + 1.0f) * r);
     const int d = k - m;
-    if (d >= -32 && d <= 32) {
+    if (lf2 != nullptr && b.n < URSM_BINOM_TABLE) {
+      // log2 f(k)/f(m) = log2 m! + log2 (n-m)! - log2 k! - log2 (n-k)! + (k - m) log2(r/(1-r))
+      const double lg = (lf2[m] + lf2[b.n - m]) - (lf2[k] + lf2[b.n - k]);
+      const float rhs = fmaf((float)d, URSM_LG2(URSM_DIV(r, b.rc)), (float)lg);
+      ok = URSM_LG2(lhs) <= rhs;
+    } else if (d >= -32 && d <= 32) {
       // f(k)/f(m) as an explicit product of at most 32 ratios (fp32, as BTPE does near
       // the mode): f(i)/f(i-1) = (n-i+1)/i * r/(1-r)
       const float odds = URSM_DIV(r, b.rc);
@@ -512,17 +529,84 @@ URSM_HD void binom_btrs_attempt(BinomState& b, float U, float V) {
   }
 }
 
-// run the state machine to completion (host tests; same arithmetic as the kernel)
+// ---------------------------------------------------------------------------
+// Binomial(n, r), 0 < r <= 1/2, by inversion FROM THE MODE (Kemp 1986's modal search):
+// the atoms are visited in the fixed order m, m+1, m-1, m+2, m-2, ... (m = floor((n+1) r))
+// and the uniform is compared with their masses one after the other -- a valid inversion
+// for any visiting order that does not depend on the uniform.  Expected atoms visited
+// ~ 1 + 1.6 sqrt(n r (1-r)) instead of 1 + n r for the search from 0, which is what the
+// bulk split kernel's cost per item is made of (counts of ~50 reads split over 5-10 types:
+// n r ~ 5-10).  pmf(m) = C(n,m) r^m (1-r)^(n-m) comes from a table of log2 k! (double, in
+// shared memory in the kernel) and two MUFU logarithms; neighbours by the ratio recurrences
+//     pmf(x)/pmf(x-1) = c/x - s,   pmf(x-1)/pmf(x) = x / ((n-x+1) s),  s = r/(1-r), c = (n+1) s.
+// Used for n < URSM_BINOM_TABLE and n r <= URSM_BINOM_MODE_MAX; relative error of the fp32
+// masses ~ 1e-7 (n r + 10).  Returns the draw, or -1 when the uniform lies beyond the sum of
+// the fp32 masses (probability ~1e-6): the caller retries with a fresh uniform, which keeps
+// the draw unbiased.
+// ---------------------------------------------------------------------------
+URSM_HD int binom_mode_try(int n, float r, float rc, float u, const double* lf2) {
+  const float nf = (float)n;
+  int m = (int)((nf + 1.0f) * r);
+  m = m < n ? m : n;
+  const float mf = (float)m;
+  // log2(1 - r): series below r = 1/16 (relative error < 1e-8), MUFU on the complement above
+  const float ser = -r * fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, 1.0f / 6, 0.2f), 0.25f), 1.0f / 3),
+                                      0.5f), 1.0f);
+  const float l2rc = (r < 0.0625f) ? 1.4426950408889634f * ser : URSM_LG2(rc);
+  const float logc = (float)(lf2[n] - lf2[m] - lf2[n - m]);  // log2 C(n, m)
+  const float pm = URSM_EX2(fmaf(nf - mf, l2rc, fmaf(mf, URSM_LG2(r), logc)));
+  if (u <= pm) return m;
+  u -= pm;
+  const float t = URSM_RCP(r * rc);
+  const float s = r * r * t, is = rc * rc * t;  // r/(1-r) and its reciprocal
+  const float c = (nf + 1.0f) * s;
+  float pu = pm, pd = pm, fu = mf, fd = mf;    // masses and positions of the two cursors
+  while (true) {
+    const bool up = fu < nf && pu > 1e-30f, dn = fd > 0.0f && pd > 1e-30f;
+    if (up) {
+      fu += 1.0f;
+      pu *= fmaf(c, URSM_RCP(fu), -s);
+      if (u <= pu) return (int)fu;
+      u -= pu;
+    }
+    if (dn) {
+      pd *= fd * is * URSM_RCP(nf - fd + 1.0f);
+      fd -= 1.0f;
+      if (u <= pd) return (int)fd;
+      u -= pd;
+    }
+    if (!up && !dn) return -1;
+  }
+}
+
+// log2 k!, k = 0 .. URSM_BINOM_TABLE-1 (host side; the kernels stage a copy in shared memory)
+inline void binom_fill_table(double* lf2) {
+  for (int k = 0; k < URSM_BINOM_TABLE; ++k) lf2[k] = lgamma((double)k + 1.0) / 0.6931471805599453;
+}
+
+// which sampler the bulk split kernel uses for Bin(n, r), r <= 1/2
+URSM_HD bool binom_use_mode(int n, float nr) {
+  return n < URSM_BINOM_TABLE && nr <= URSM_BINOM_MODE_MAX;
+}
+
+// run the samplers to completion (host tests; same arithmetic and dispatch as the kernel)
 template <class RNG>
-URSM_HD int binomial_f32(int n, float p, float pc, RNG& rng) {
+URSM_HD int binomial_f32(int n, float p, float pc, RNG& rng, const double* lf2) {
   BinomState b;
+  const bool flip = p > 0.5f;
+  const float r = flip ? pc : p, rc = flip ? p : pc;
+  if (n > 0 && r > 0.0f && binom_use_mode(n, (float)n * r)) {
+    int x = binom_mode_try(n, r, rc, rng.uniform(), lf2);
+    for (int guard = 0; guard < 1000 && x < 0; ++guard) x = binom_mode_try(n, r, rc, rng.uniform(), lf2);
+    return flip ? n - x : x;
+  }
   binom_begin(b, n, p, pc, rng.uniform());
   for (int guard = 0; guard < 100000 && b.mode != kBinDone; ++guard) {
     if (b.mode == kBinInv) {
       binom_inv_chunk4(b);
     } else if (b.mode == kBinBtrs) {
       const float U = rng.uniform(), V = rng.uniform();
-      binom_btrs_attempt(b, U, V);
+      binom_btrs_attempt(b, U, V, lf2);
     } else {  // kBinRetry
       binom_inv_start(b, rng.uniform());
     }

@@ -49,12 +49,15 @@ struct BkShard {
   long long sample_offset = 0;
   DevBuf<float> Xown;
   const float* X = nullptr;      // [M][N] counts
-  DevBuf<float> Xs;              // [M][N] columns sorted by total count (Gibbs split kernel)
-  DevBuf<int> perm;              // [N] sorted position -> gene
+  DevBuf<float> Xt;              // [N][Mpad] gene-major copy (Gibbs split kernel: lanes = samples)
+  int Mpad = 0;                  // M rounded up to a multiple of 32
+  DevBuf<float> A32;             // [K][N] fp32 A^T
+  DevBuf<float> W32g;            // [ceil(M/32)][K][32] fp32 W of the current sweep
   DevBuf<double> A;              // [K][N] type-major fp64
   DevBuf<double> alpha;          // [K]
   DevBuf<double> W;              // [M][K] (sample-major)
-  DevBuf<double> nA, nB;         // [M][K] sum_i Z_jik: previous / being built
+  DevBuf<double> nA, nB;         // [M][K] sum_i Z_jik: previous sweep / being built
+  DevBuf<double> lf2;            // [1024] log2 k! (modal binomial inversion)
   DevBuf<double> acc;            // [M][K] scratch (nmf numerators)
   DevBuf<double> eZjk, eLogW, eW;  // [M][K] each
   bool has_params = false, has_state = false;

@@ -230,7 +230,9 @@ class LogitNormalGEM(object):
     def em_iteration(self):
         """One body of the reference's while loop (gem.py:163-192); returns
         (elbo after the E-step, elbo after the M-step)."""
+        ev = self._events_begin()
         self.estep_gibbs()
+        self._events_mark(ev)
         self.mle.update_suff_stats(self.suff_stats)
         elbo_e = self.mle.compute_elbo()
         logging.info("\tE-step finished: elbo=%.6f", elbo_e)
@@ -244,8 +246,31 @@ class LogitNormalGEM(object):
         self.mle.opt_A_u()
         self.A = self.mle.A
         elbo = self.mle.compute_elbo()
+        self._events_mark(ev)
         logging.info("\tM-step finished: elbo=%.6f", elbo)
         return elbo_e, elbo
+
+    # optional device-side timing of an EM iteration (bench.py): `record_events = True` makes
+    # em_iteration append [start, after the E-step, end] CUDA events to `self.events`
+    record_events = False
+
+    def _events_begin(self):
+        if not self.record_events:
+            return None
+        import torch
+        ev = [torch.cuda.Event(enable_timing=True)]
+        ev[0].record()
+        if not hasattr(self, "events"):
+            self.events = []
+        self.events.append(ev)
+        return ev
+
+    def _events_mark(self, ev):
+        if ev is not None:
+            import torch
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append(e)
 
     def gem(self):
         (converged, niter) = (self.EM_CONV + 1, 0)
