@@ -212,6 +212,16 @@ int ursm_mle_opt_merge_p2p(ursm_mle* m, double* d_part, void* stream);
 int ursm_mle_p2p_error(ursm_mle* m, int32_t* h_err);
 int ursm_mle_opt_poll(ursm_mle* m, int32_t* h_active, int32_t* h_niter, int32_t* h_halvings,
                       double* h_delta, void* stream);
+/* opt_A_u :128-154 for the columns flagged in h_active, run to completion in one call: the
+ * loop of opt_Ak :157-182 lives on the device (16 outer iterations per launch of a captured
+ * CUDA graph on the workspace's own stream: step + decision + installation in one kernel, then
+ * the opt_u / update_gd_coeffConst pass; with the peer exchange opened, the cross-rank sum of
+ * every iteration inside the same graph).  d_part_init = the all-reduced partials of the pass
+ * before the loop (ursm_mle_pass_u); the caller runs that full pass again afterwards (it also
+ * refreshes sum_l R_l log u_l).  h_niter / h_halvings: per column, as ursm_mle_opt_poll. */
+int ursm_mle_opt_run(ursm_mle* m, const int32_t* h_active, double init_step, double conv,
+                     int32_t maxiter, const double* d_part_init, int32_t* h_niter,
+                     int32_t* h_halvings, int32_t* h_graph_launches, void* stream);
 int ursm_mle_closed_form(ursm_mle* m, int32_t k, const double* d_exp_Zik, void* stream);
 int ursm_mle_elbo_terms(ursm_mle* m, const double* d_cconst_part, double* h_terms3,
                         void* stream);

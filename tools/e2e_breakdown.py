@@ -96,6 +96,42 @@ def main():
     for n, v in zip(names, tm):
         print("%-24s %8.2f ms" % (n, v))
     print("%-24s %8.2f ms" % ("total", tm.sum()))
+    # ---- steady state: one model, repeated EM iterations (bench.py's device-timed arm)
+    g = LogitNormalGEM(BKexpr=nX, SCexpr=nY, K=K, G=G, burnin=cfg["burnin"], sample=cfg["sample"],
+                       thin=1, bk_mean_approx=(args.bulk_mode == "mean"), MLE_CONV=1e-6,
+                       MLE_maxiter=500, EM_CONV=1e-6, EM_maxiter=10 ** 6, seed=1)
+    g.init_gibbs()
+    g.init_mle()
+    rows = []
+    for it in range(2 + args.reps):
+        t = [sync()]
+        g.estep_gibbs()
+        t.append(sync())
+        g.mle.update_suff_stats(g.suff_stats)
+        t.append(sync())
+        g.mle.compute_elbo()
+        t.append(sync())
+        if g.hasSC:
+            g.mle.opt_kappa_tau()
+            g.pkappa, g.ptau = g.mle.pkappa, g.mle.ptau
+        if g.hasBK:
+            g.mle.opt_alpha()
+            g.alpha = g.mle.alpha
+        t.append(sync())
+        g.mle.opt_A_u()
+        g.A = g.mle.A
+        t.append(sync())
+        g.mle.compute_elbo()
+        t.append(sync())
+        if it >= 2:
+            rows.append(np.diff(t))
+    tm = np.median(np.array(rows), axis=0) * 1e3
+    print("steady state (same model, EM iterations 3..):")
+    for n, v in zip(["estep", "update_suff_stats", "elbo", "kappa_tau+alpha (host)", "opt_A_u", "elbo"], tm):
+        print("  %-24s %8.2f ms" % (n, v))
+    print("  outer iterations %s, graph launches %s" % (list(g.mle.niter_A),
+                                                        getattr(g.mle, "graph_launches", None)))
+    del g
     pr = cProfile.Profile()
     pr.enable()
     step(None)

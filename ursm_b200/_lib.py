@@ -66,6 +66,7 @@ SIGNATURES = {
     "ursm_mle_opt_pass": (c_int, [c_vp, c_vp, c_vp]),
     "ursm_mle_opt_merge": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_opt_poll": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ursm_mle_opt_run": (c_int, [c_vp, c_vp, c_dbl, c_dbl, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_p2p_alloc": (c_int, [c_vp, c_vp, c_vp]),
     "ursm_mle_p2p_state": (c_int, [c_vp, c_vp]),
     "ursm_mle_p2p_reset": (c_int, [c_vp]),

@@ -45,6 +45,30 @@ struct Mle {
   int num_sms = 148;
   // peer-memory exchange of the per-iteration partials (ursm_mle_p2p_*)
   struct P2PBlock* p2p = nullptr;
+  // device-resident loop of opt_Ak (ursm_mle_opt_run): its own stream, the captured graph of
+  // kGraphIters outer iterations, double-buffered partials, per-column arrival counters
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  struct GraphKey {
+    double init_step = 0, conv = 0;
+    int maxiter = 0, ncand = 0, p2p = 0, cnt_w = 0, sample = 0, y_smem = 0;
+    const void* coeffs = nullptr;
+    const void* p2p_own = nullptr;
+    const void* act = nullptr;
+    const void* cnt = nullptr;
+    bool operator==(const GraphKey& o) const {
+      return init_step == o.init_step && conv == o.conv && maxiter == o.maxiter && ncand == o.ncand &&
+             p2p == o.p2p && cnt_w == o.cnt_w && sample == o.sample && y_smem == o.y_smem &&
+             coeffs == o.coeffs && p2p_own == o.p2p_own && act == o.act && cnt == o.cnt;
+    }
+  } gkey;
+  DevBuf<double> partbuf;                // [2][K*N + K] (single rank) / [1][...] summed partials (peers)
+  DevBuf<int> done;                      // [K] cand CTAs of a column that have finished
+  DevBuf<double> lam_store;              // [K][kCand] projection multipliers of the previous iteration
+  DevBuf<double> gbuf, gobj;             // [K][N] gradient; [K][ceil(N/256)][3] objective partials
+  DevBuf<unsigned long long> epoch_dev;  // [1] epoch of the peer exchange at the start of a graph launch
+  int* h_poll = nullptr;                 // pinned: [K] act | [K] niter | [K] halv
   ~Mle();
 };
 
@@ -68,7 +92,14 @@ static std::vector<P2PBlock*> g_p2p_blocks;
 
 Mle::~Mle() {
   if (p2p) p2p->in_use = false;
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (ev_in) cudaEventDestroy(ev_in);
+  if (ev_out) cudaEventDestroy(ev_out);
+  if (gstream) cudaStreamDestroy(gstream);
+  if (h_poll) cudaFreeHost(h_poll);
 }
+
+constexpr int kGraphIters = 16;  // outer iterations per graph launch (even: buffer parity is static)
 
 constexpr int kCand = 16;  // trial step sizes of backtracking evaluated concurrently
 
@@ -302,6 +333,104 @@ mle_u_kernel(const CT* cnt, const int* order, const int* type_start, const doubl
   }
 }
 
+// opt_u (:108-115) + update_gd_coeffConst (:118-125) in ONE pass for gene vectors short enough
+// that a block of cells' counter rows fits in shared memory (N <= 8192: c2, c5): a CTA takes
+// `nc` consecutive cells of the type-sorted order; per run of same-type cells, (1) its warps
+// stream the rows once from HBM / L2 -- 8 bytes per lane and load -- into shared memory while
+// accumulating the row dot with A[:, type] (u_l), (2) the threads then own groups of 8 bytes of
+// adjacent counters and sum the staged rows, weighted by R_l / u_l, into one atomic per gene and
+// CTA.  The counters cross the memory system once per outer iteration (the two-kernel path reads
+// them twice) and there is one launch instead of two.
+constexpr int kFusedThreads = 512;
+
+template <class CT>
+__global__ void __launch_bounds__(kFusedThreads, 2)
+mle_pass_fused_kernel(const CT* cnt, const int* order, const int* type_start, const double* A,
+                      const int* active, const double* R, double* u, long long L, int N, int K,
+                      int nc, double inv_sample, double* out) {
+  constexpr int C8 = 8 / (int)sizeof(CT);    // counters per 8-byte load / group
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kFusedThreads >> 5;
+  const size_t row_bytes = (size_t)N * sizeof(CT);  // a multiple of 8, N even (host checks)
+  double* w_s = reinterpret_cast<double*>(fused_smem);           // [nc] R_l / u_l / sample
+  double* dot_s = w_s + nc;                                       // [nc][2] half-row dot products
+  unsigned char* rows = fused_smem + (((size_t)nc * 24 + 15) & ~(size_t)15);  // [nc][row_bytes]
+  const long long c_lo = (long long)blockIdx.x * nc, c_hi = min(L, c_lo + nc);
+  for (int k = 0; k < K; ++k) {
+    const long long lo = max(c_lo, (long long)type_start[k]);
+    const long long hi = min(c_hi, (long long)type_start[k + 1]);
+    if (lo >= hi || !active[k]) continue;
+    const double* Ak = A + (size_t)k * N;
+    // ---- phase 1: stage the rows, row dots.  Two warps per row (interleaved 8-byte loads,
+    // eight in flight per lane: the pass is a chain of memory round trips, not arithmetic)
+    for (long long cb = lo; cb < hi; cb += nwarp / 2) {
+      const long long c = cb + (warp >> 1);
+      const int half = warp & 1;
+      if (c < hi) {
+        const int l = order[c];
+        const uint2* src = reinterpret_cast<const uint2*>(cnt + (size_t)l * N);
+        uint2* dst = reinterpret_cast<uint2*>(rows + (size_t)(c - c_lo) * row_bytes);
+        const int nv = (int)(row_bytes >> 3);
+        double acc = 0.0;
+        for (int v0 = half * 32 + lane; v0 < nv; v0 += 64 * 8) {
+          uint2 x[8];
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const int v = v0 + 64 * h;
+            x[h] = v < nv ? src[v] : make_uint2(0u, 0u);
+          }
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const int v = v0 + 64 * h;
+            if (v >= nv) break;
+            dst[v] = x[h];
+            double e[C8];
+            CntVec<CT>::unpack(x[h], e);
+            const double2* a2 = reinterpret_cast<const double2*>(Ak + (size_t)v * C8);
+#pragma unroll
+            for (int q = 0; q < C8 / 2; ++q) {
+              const double2 p = a2[q];
+              acc = fma(p.x, e[2 * q], acc);
+              acc = fma(p.y, e[2 * q + 1], acc);
+            }
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) dot_s[2 * (c - c_lo) + half] = acc;
+      }
+    }
+    __syncthreads();
+    for (long long c = lo + tid; c < hi; c += kFusedThreads) {
+      const int l = order[c];
+      const double ul = (dot_s[2 * (c - c_lo)] + dot_s[2 * (c - c_lo) + 1]) * inv_sample;
+      u[l] = ul;
+      w_s[c - c_lo] = (R[l] / ul) * inv_sample;
+    }
+    __syncthreads();
+    // ---- phase 2: weighted column sums of the staged rows
+    const int ngrp = (int)(row_bytes >> 3);
+    for (int gq = tid; gq < ngrp; gq += kFusedThreads) {
+      double acc[C8];
+#pragma unroll
+      for (int q = 0; q < C8; ++q) acc[q] = 0.0;
+      for (long long c = lo; c < hi; ++c) {
+        const uint2 v = *reinterpret_cast<const uint2*>(rows + (size_t)(c - c_lo) * row_bytes +
+                                                        (size_t)gq * 8);
+        const double w = w_s[c - c_lo];
+        double e[C8];
+        CntVec<CT>::unpack(v, e);
+#pragma unroll
+        for (int q = 0; q < C8; ++q) acc[q] = fma(e[q], w, acc[q]);
+      }
+      double* o = out + (size_t)k * N + (size_t)gq * C8;
+#pragma unroll
+      for (int q = 0; q < C8; ++q)
+        if (acc[q] != 0.0) atomicAdd(o + q, acc[q]);
+    }
+    __syncthreads();
+  }
+}
+
 // out[type] = sum_{l in type} R_l log u_l   (compute_elbo :308), every type
 __global__ void mle_rlogu_kernel(const int* G, const double* R, const double* u, long long L,
                                  double* out) {
@@ -326,13 +455,27 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* red) {
   b = warp_sum(z);
 }
 
-// lambda such that sum_i max(y_i + lambda, m) = 1  (utils.py:8-31 without the sort)
-__device__ double proj_lambda(const double* y, int N, double m, double* red) {
+// lambda such that sum_i max(y_i + lambda, m) = 1  (utils.py:8-31 without the sort).
+// Michelot's active-set iteration = Newton's method on the convex piecewise-linear
+// f(lambda) = sum_i max(y_i + lambda, m) - 1: from ANY start the first step lands at or above
+// the root and the iterates then decrease to it in finitely many steps; the active sets
+// {y_i + lambda > m} are threshold sets, hence nested, so an unchanged count means an unchanged
+// set and the lambda computed from it is final.  `warm` (may be null / NaN) is a guess -- the
+// lambda of the same trial in the previous outer iteration -- that replaces the cold start
+// (every entry active) and saves most of the passes; the result is the same lambda, summed in
+// the same order.
+__device__ double proj_lambda(const double* y, int N, double m, double* red,
+                              const double* warm = nullptr) {
   double s = 0.0, c = 0.0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) s += y[i];
-  s = block_sum(s, red);
-  double lam = (1.0 - s) / N;
-  double prev = N;
+  double lam = warm ? *warm : nan("");
+  double prev = -1.0;
+  bool cold = !(lam == lam);
+  if (cold) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s += y[i];
+    s = block_sum(s, red);
+    lam = (1.0 - s) / N;
+    prev = N;
+  }
   for (int it = 0; it < 4096; ++it) {
     s = 0.0;
     c = 0.0;
@@ -344,7 +487,17 @@ __device__ double proj_lambda(const double* y, int N, double m, double* red) {
       }
     }
     block_sum2(s, c, red);
-    if (c == 0.0) break;  // degenerate (N*m >= 1): everything sits on the floor
+    if (c == 0.0) {
+      if (cold) break;  // degenerate (N*m >= 1): everything sits on the floor
+      // a guess so low that nothing is active: start over from the cold start
+      s = 0.0;
+      for (int i = threadIdx.x; i < N; i += blockDim.x) s += y[i];
+      s = block_sum(s, red);
+      lam = (1.0 - s) / N;
+      prev = N;
+      cold = true;
+      continue;
+    }
     lam = (1.0 - (N - c) * m - s) / c;
     if (c == prev) break;
     prev = c;
@@ -365,6 +518,22 @@ struct StepArgs {
   int N;
   double min_A, init_step;
   int y_smem;          // trial column lives in dynamic shared memory (N doubles)
+  // fused loop (ursm_mle_opt_run; all null / 0 in the step-by-step entry points):
+  double* Aw;          // [K][N] writable alias of A: the last CTA of a column installs the winner
+  double* zero_out;    // [K*N + K] partials buffer of the pass that follows: zeroed here
+  double* u_acc;       // [L] partial dot products of the pass that follows: zeroed here
+  const int* order;    // [L] cells sorted by type
+  const int* type_start;  // [K+1]
+  int* done;           // [K] arrival counters
+  int* act_w;          // [K] loop state, advanced in place by the last CTA of a column
+  int *niter, *halv, *base_w;
+  double* delta;
+  double* lam_store;   // [K][kCand] lambda of each trial in the previous outer iteration (warm start)
+  const double* gbuf;  // [K][N] gradient of the current columns (mle_grad_kernel), or null
+  const double* gobj;  // [K][gslots][3] block partials of the current objective
+  int gslots;
+  double conv;
+  int maxiter, ncand, K;
 };
 
 __device__ __forceinline__ void block_sum6(double* v, double* red) {
@@ -381,6 +550,37 @@ __device__ __forceinline__ void block_sum6(double* v, double* red) {
   for (int q = 0; q < 6; ++q) v[q] = warp_sum((lane < nw) ? red[q * 32 + lane] : 0.0);
 }
 
+// What every trial of a column shares (fused loop): the gradient -get_grad_A (:262-272) and the
+// three sums of the current objective -get_obj_A (:275-287).  One thread per gene over the whole
+// machine instead of once per trial CTA (16 x the fp64 log / divide work on 1/16 of the SMs);
+// the block partials go to fixed slots that the trial CTAs add up in a fixed order.
+constexpr int kGradThreads = 256;
+
+__global__ void __launch_bounds__(kGradThreads)
+mle_grad_kernel(const double* A, const double* cAinv, const double* cA, const double* coeffA,
+                const double* part, const int* act, int N, double* gbuf, double* gobj) {
+  __shared__ double red[6 * 32];
+  const int k = blockIdx.y;
+  if (!act[k]) return;
+  const int i = blockIdx.x * kGradThreads + threadIdx.x;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  if (i < N) {
+    const size_t e = (size_t)k * N + i;
+    const double x = A[e], cc = coeffA[e] - part[e];
+    gbuf[e] = -((cAinv[e] / x + cA[e] * x + cc) * (1.0 / N));
+    v[0] = cAinv[e] * log(x);
+    v[1] = cA[e] * x * x;
+    v[2] = cc * x;
+  }
+  block_sum6(v, red);
+  if (threadIdx.x == 0) {
+    double* o = gobj + ((size_t)k * gridDim.x + blockIdx.x) * 3;
+    o[0] = v[0];
+    o[1] = v[1];
+    o[2] = v[2];
+  }
+}
+
 // One trial of backtracking (:209-233) per CTA: column blockIdx.y, step size
 // init_step / 2^(base + blockIdx.x).  The reference halves sequentially until the
 // sufficient-decrease test passes; the kCand trials of a batch are independent, so
@@ -390,9 +590,21 @@ __device__ __forceinline__ void block_sum6(double* v, double* red) {
 //   projection = simplex_proj (utils.py:8-31) via proj_lambda.
 __global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
   __shared__ double red[6 * 32];
+  __shared__ int last_s;
   extern __shared__ double cand_ysm[];
   const int k = blockIdx.y, c = blockIdx.x, N = a.N, tid = threadIdx.x, T = blockDim.x;
+  if (a.zero_out && c == 0 && tid == 0) a.zero_out[(size_t)a.K * N + k] = 0.0;  // sum_l R_l log u_l
   if (!a.act[k]) return;
+  if (a.zero_out) {
+    // what the pass after this step accumulates into, for this column: slice c of the
+    // partials row and of the per-cell dot products of the column's cells
+    const int nc = gridDim.x;
+    const int i0 = (int)((long long)N * c / nc), i1 = (int)((long long)N * (c + 1) / nc);
+    for (int i = i0 + tid; i < i1; i += T) a.zero_out[(size_t)k * N + i] = 0.0;
+    const long long t0 = a.type_start[k], t1 = a.type_start[k + 1];
+    const long long l0 = t0 + (t1 - t0) * c / nc, l1 = t0 + (t1 - t0) * (c + 1) / nc;
+    for (long long l = l0 + tid; l < l1; l += T) a.u_acc[a.order[l]] = 0.0;
+  }
   const double* Ak = a.A + (size_t)k * N;
   double* yout = a.cand + ((size_t)k * kCand + c) * N;
   // the trial column is re-read by every pass of the projection: keep it on chip
@@ -403,23 +615,38 @@ __global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
   const double* pt = a.part + (size_t)k * N;
   const double invN = 1.0 / N;
   const double step = ldexp(a.init_step, -(a.base[k] + c));
+  const double* gk = a.gbuf ? a.gbuf + (size_t)k * N : nullptr;
   double v[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = tid; i < N; i += T) {
-    const double x = Ak[i], cc = c0[i] - pt[i];
-    const double g = -((ci[i] / x + ca[i] * x + cc) * invN);
-    y[i] = x - step * g;
-    v[0] += ci[i] * log(x);
-    v[1] += ca[i] * x * x;
-    v[2] += cc * x;
+  if (gk) {  // gradient and current objective precomputed once per column (mle_grad_kernel)
+    for (int i = tid; i < N; i += T) y[i] = Ak[i] - step * gk[i];
+    if (tid < 32) {
+      const double* o = a.gobj + (size_t)k * a.gslots * 3;
+      for (int q = tid; q < a.gslots; q += 32) {  // fixed order: lane q takes slots q, q+32, ...
+        v[0] += o[3 * q];
+        v[1] += o[3 * q + 1];
+        v[2] += o[3 * q + 2];
+      }
+    }
+  } else {
+    for (int i = tid; i < N; i += T) {
+      const double x = Ak[i], cc = c0[i] - pt[i];
+      const double g = -((ci[i] / x + ca[i] * x + cc) * invN);
+      y[i] = x - step * g;
+      v[0] += ci[i] * log(x);
+      v[1] += ca[i] * x * x;
+      v[2] += cc * x;
+    }
   }
   block_sum6(v, red);
   const double obj_old = -((v[0] + v[1] / 2.0 + v[2]) * invN);
   __syncthreads();
-  const double lam = proj_lambda(y, N, a.min_A, red);
+  double* lam_slot = a.lam_store ? a.lam_store + (size_t)k * kCand + c : nullptr;
+  const double lam = proj_lambda(y, N, a.min_A, red, lam_slot);
+  if (lam_slot && tid == 0) *lam_slot = lam;
   for (int q = 0; q < 6; ++q) v[q] = 0.0;
   for (int i = tid; i < N; i += T) {
     const double x = Ak[i], cc = c0[i] - pt[i];
-    const double g = -((ci[i] / x + ca[i] * x + cc) * invN);
+    const double g = gk ? gk[i] : -((ci[i] / x + ca[i] * x + cc) * invN);
     const double nv = fmax(y[i] + lam, a.min_A);
     const double Gt = (x - nv) / step;
     yout[i] = nv;
@@ -440,6 +667,42 @@ __global__ void __launch_bounds__(1024) mle_cand_kernel(StepArgs a) {
     r[2] = v[5];
     r[3] = step;
   }
+  if (!a.done) return;
+  // ---- fused loop: the LAST trial CTA of the column to finish decides (the first passing
+  // trial = the step the sequential halving accepts, :209-233), advances the opt_Ak loop
+  // state (:164-181) and installs the accepted column
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_s = (atomicAdd(&a.done[k], 1) == a.ncand - 1) ? 1 : 0;
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  if (tid == 0) {
+    a.done[k] = 0;
+    int w = -1;
+    for (int q = 0; q < a.ncand; ++q)
+      if (a.cres[((size_t)k * kCand + q) * 4] != 0.0) {
+        w = q;
+        break;
+      }
+    if (w < 0 && a.base_w[k] + a.ncand >= 1024) w = a.ncand - 1;  // step underflow guard
+    if (w < 0) {  // every trial of this batch was rejected: keep halving
+      a.base_w[k] += a.ncand;
+    } else {
+      const double d = a.cres[((size_t)k * kCand + w) * 4 + 2];
+      a.delta[k] = d;
+      a.halv[k] += a.base_w[k] + w;
+      a.base_w[k] = 0;
+      const int n = ++a.niter[k];
+      a.act_w[k] = (d > a.conv && n < a.maxiter) ? 1 : 0;
+    }
+    last_s = w;
+  }
+  __syncthreads();
+  const int w = last_s;
+  if (w < 0) return;
+  const double* src = a.cand + ((size_t)k * kCand + w) * N;
+  for (int i = tid; i < N; i += T) a.Aw[(size_t)k * N + i] = src[i];
 }
 
 // One CTA per column: thread 0 accepts the first passing trial of the batch (or schedules
@@ -512,7 +775,8 @@ struct P2PArgs {
   unsigned long long* peer_flags[kMaxPeers];  // peer r's flag array (we write entry `rank`)
   const unsigned long long* my_flags;   // [world] written by the peers
   int world, rank;
-  unsigned long long epoch;
+  unsigned long long epoch;                 // epoch of this exchange, or (fused loop) its offset ...
+  const unsigned long long* epoch_base;     // ... from the device-resident base (null: absolute)
   int* err;
 };
 
@@ -531,13 +795,15 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
 }
 
 __global__ void mle_p2p_merge_kernel(P2PArgs a, double* part, const int* act, int N, int K) {
+  const unsigned long long epoch = a.epoch + (a.epoch_base ? *a.epoch_base : 0ull);
   if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < a.world) {
     __threadfence_system();
-    st_release_sys(a.peer_flags[threadIdx.x] + a.rank, a.epoch);
+    st_release_sys(a.peer_flags[threadIdx.x] + a.rank, epoch);
   }
   if ((int)threadIdx.x < a.world) {
     const long long t0 = clock64();
-    while (ld_acquire_sys(a.my_flags + threadIdx.x) < a.epoch) {
+    // a barrier that timed out once poisons the block: later launches do not wait again
+    while (ld_acquire_sys(a.my_flags + threadIdx.x) < epoch && *((volatile int*)a.err) == 0) {
       if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer is gone; fail loudly instead of hanging
         *a.err = 1;
         break;
@@ -562,6 +828,8 @@ __global__ void mle_p2p_merge_kernel(P2PArgs a, double* part, const int* act, in
     part[(size_t)k * N + i] = s;
   }
 }
+
+__global__ void mle_epoch_bump_kernel(unsigned long long* epoch, unsigned long long by) { *epoch += by; }
 
 // A_k = simplex_proj(v / sum v)   (m_step.py:149-153, utils.py:8-31)
 __global__ void __launch_bounds__(1024)
@@ -727,13 +995,68 @@ int ursm_mle_begin(ursm_mle* mm, double* d_part, void* stream) {
   URSM_API_END
 }
 
-// opt_u + update_gd_coeffConst for the columns flagged in m->act_cur (device flags)
-static void mle_pass(Mle* m, double* d_part, cudaStream_t st) {
+// The one-pass kernel applies when rows keep 8-byte alignment and a useful block of cells fits
+// in shared memory next to two resident CTAs per SM (URSM_MLE_FUSED=0 forces the two-kernel path).
+static bool mle_fused_ok(const Mle* m) {
+  if (const char* e = getenv("URSM_MLE_FUSED"))
+    if (!atoi(e)) return false;
+  const size_t row_bytes = (size_t)m->N * m->sc->cnt_w;
+  return (row_bytes % 8) == 0 && (m->N % 2) == 0 && m->N <= 8192;
+}
+
+static void mle_fused_geometry(const Mle* m, int* nc_out, size_t* smem_out) {
+  const size_t row_bytes = (size_t)m->N * m->sc->cnt_w;
+  const long long cap = std::max<long long>(1, (long long)(100 * 1024) / (long long)row_bytes);
+  int per_sm = 2;  // CTAs per SM the grid aims at: their phases overlap
+  if (const char* e = getenv("URSM_MLE_FUSED_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+  const long long slots = (long long)per_sm * m->num_sms;
+  long long nc = (m->sc->L + slots - 1) / slots;
+  nc = std::max<long long>(std::min<long long>(nc, cap), std::min<long long>(8, cap));
+  const size_t smem = (((size_t)nc * 24 + 15) & ~(size_t)15) + (size_t)nc * row_bytes;
+  static size_t configured[2] = {0, 0};
+  const int which = m->sc->cnt_w == 1 ? 0 : 1;
+  if (smem > 48 * 1024 && smem > configured[which]) {
+    if (which == 0)
+      URSM_CUDA(cudaFuncSetAttribute(mle_pass_fused_kernel<unsigned char>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      URSM_CUDA(cudaFuncSetAttribute(mle_pass_fused_kernel<unsigned short>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[which] = smem;
+  }
+  *nc_out = (int)nc;
+  *smem_out = smem;
+}
+
+// opt_u + update_gd_coeffConst for the columns flagged in m->act_cur (device flags).
+// `lean`: the fused loop -- the buffers were zeroed by the step kernel and sum_l R_l log u_l is
+// left to the full pass that follows the loop.
+static void mle_pass(Mle* m, double* d_part, cudaStream_t st, bool lean = false) {
   ScShard* s = m->sc;
   const size_t KN = (size_t)m->K * m->N;
-  URSM_CUDA(cudaMemsetAsync(d_part, 0, (KN + m->K) * sizeof(double), st));
+  if (!lean) URSM_CUDA(cudaMemsetAsync(d_part, 0, (KN + m->K) * sizeof(double), st));
   const double inv = 1.0 / s->sample;
   URSM_REQUIRE(s->cnt_w > 0, "M-step: the single-cell E-step has not run yet");
+  if (mle_fused_ok(m)) {
+    int nc;
+    size_t smem;
+    mle_fused_geometry(m, &nc, &smem);
+    const unsigned nb = (unsigned)((s->L + nc - 1) / nc);
+    if (s->cnt_w == 1)
+      mle_pass_fused_kernel<unsigned char><<<nb, kFusedThreads, smem, st>>>(
+          s->cnt.p, s->order.p, m->type_start.p, m->A.p, m->act_cur.p, s->R.p, m->u.p, s->L, m->N,
+          m->K, nc, inv, d_part);
+    else
+      mle_pass_fused_kernel<unsigned short><<<nb, kFusedThreads, smem, st>>>(
+          reinterpret_cast<const unsigned short*>(s->cnt.p), s->order.p, m->type_start.p, m->A.p,
+          m->act_cur.p, s->R.p, m->u.p, s->L, m->N, m->K, nc, inv, d_part);
+    URSM_LAUNCH_CHECK();
+    if (lean) return;
+    mle_rlogu_kernel<<<(unsigned)((s->L + 255) / 256), 256, 0, st>>>(s->G.p, s->R.p, m->u.p, s->L,
+                                                                    d_part + KN);
+    URSM_LAUNCH_CHECK();
+    return;
+  }
   const int C = 8 / s->cnt_w;
   const int gx = (m->N + C * kColThreads - 1) / (C * kColThreads);
   int ny;
@@ -749,7 +1072,7 @@ static void mle_pass(Mle* m, double* d_part, cudaStream_t st) {
     nseg = (int)std::min<long long>((m->N + 127) / 128, (4LL * m->num_sms + ub - 1) / ub);
   const int seg_genes = std::min(kUSegGenes, ((m->N + nseg - 1) / nseg + 127) / 128 * 128);
   nseg = (m->N + seg_genes - 1) / seg_genes;
-  m->ratio.zero(st);  // u_acc: partial dot products
+  if (!lean) m->ratio.zero(st);  // u_acc: partial dot products
   if (s->cnt_w == 1) {
     mle_u_kernel<unsigned char><<<dim3(ub, nseg), kUThreads, 0, st>>>(
         s->cnt.p, s->order.p, m->type_start.p, m->A.p, m->act_cur.p, s->L, m->N, m->K, (int)rows,
@@ -770,6 +1093,7 @@ static void mle_pass(Mle* m, double* d_part, cudaStream_t st) {
         inv, d_part);
     URSM_LAUNCH_CHECK();
   }
+  if (lean) return;
   mle_rlogu_kernel<<<(unsigned)((s->L + 255) / 256), 256, 0, st>>>(s->G.p, s->R.p, m->u.p, s->L,
                                                                   d_part + KN);
   URSM_LAUNCH_CHECK();
@@ -815,45 +1139,61 @@ int ursm_mle_opt_begin(ursm_mle* mm, const int32_t* h_active, double init_step, 
   URSM_API_END
 }
 
-int ursm_mle_opt_step(ursm_mle* mm, const double* d_cconst_part, void* stream) {
-  URSM_API_BEGIN
-  Mle* m = reinterpret_cast<Mle*>(mm);
-  URSM_REQUIRE(m && d_cconst_part && m->cAinv && m->maxiter > 0, "ursm_mle_opt_step: bad argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  StepArgs a;
+// a batch is ncand <= kCand trial steps per column, sized so that all ncand x K CTAs are
+// resident in one wave (the accepted step does not depend on the batch size)
+static int mle_ncand(const Mle* m) { return std::max(1, std::min(kCand, m->num_sms / m->K)); }
+
+// trial column in dynamic shared memory (N doubles) when it fits; opt in once, outside captures
+static int mle_cand_y_smem(const Mle* m) {
+  const size_t ybytes = (size_t)m->N * sizeof(double);
+  int y_smem = ybytes <= (size_t)160 * 1024 ? 1 : 0;
+  if (const char* e = getenv("URSM_MLE_Y_SMEM"))  // tests: the global-memory trial column
+    y_smem = (y_smem && atoi(e)) ? 1 : 0;
+  static size_t configured = 0;
+  if (y_smem && ybytes > 48 * 1024 && ybytes > configured) {
+    URSM_CUDA(cudaFuncSetAttribute(mle_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)ybytes));
+    configured = ybytes;
+  }
+  return y_smem;
+}
+
+// fills the fields every launch of the step kernel shares and launches it
+static void mle_launch_cand(Mle* m, StepArgs& a, const double* part_in, const int* act,
+                            cudaStream_t st) {
   a.A = m->A.p;
   a.cand = m->cand.p;
   a.cres = m->cres.p;
   a.cAinv = m->cAinv;
   a.cA = m->cA;
   a.coeffA = m->coeffA;
-  a.part = d_cconst_part;
-  a.act = m->act_cur.p;
+  a.part = part_in;
+  a.act = act;
   a.base = m->base.p;
   a.N = m->N;
+  a.K = m->K;
   a.min_A = m->min_A;
   a.init_step = m->init_step;
-  // a batch is ncand <= kCand trial steps per column, sized so that all ncand x K CTAs are
-  // resident in one wave (the accepted step does not depend on the batch size)
-  const int ncand = std::max(1, std::min(kCand, m->num_sms / m->K));
+  a.ncand = mle_ncand(m);
   const int T = std::max(64, std::min(1024, (m->N / 4 + 31) / 32 * 32));
-  const size_t ybytes = (size_t)m->N * sizeof(double);
-  a.y_smem = ybytes <= (size_t)160 * 1024 ? 1 : 0;
-  if (const char* e = getenv("URSM_MLE_Y_SMEM"))  // tests: the global-memory trial column
-    a.y_smem = (a.y_smem && atoi(e)) ? 1 : 0;
-  const size_t dyn = a.y_smem ? ybytes : 0;
-  static size_t configured = 0;
-  if (dyn > 48 * 1024 && dyn > configured) {
-    URSM_CUDA(cudaFuncSetAttribute(mle_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)dyn));
-    configured = dyn;
-  }
-  mle_cand_kernel<<<dim3(ncand, m->K), T, dyn, st>>>(a);
+  a.y_smem = mle_cand_y_smem(m);
+  const size_t dyn = a.y_smem ? (size_t)m->N * sizeof(double) : 0;
+  mle_cand_kernel<<<dim3(a.ncand, m->K), T, dyn, st>>>(a);
   URSM_LAUNCH_CHECK();
+}
+
+int ursm_mle_opt_step(ursm_mle* mm, const double* d_cconst_part, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && d_cconst_part && m->cAinv && m->maxiter > 0, "ursm_mle_opt_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  StepArgs a;
+  memset(&a, 0, sizeof a);
+  mle_launch_cand(m, a, d_cconst_part, m->act_cur.p, st);
   const int Tc = std::max(64, std::min(1024, (m->N / 4 + 31) / 32 * 32));
   mle_decide_copy_kernel<<<m->K, Tc, 0, st>>>(m->cres.p, m->act_cur.p, m->act_next.p, m->niter.p,
                                              m->base.p, m->halv.p, m->delta.p, m->A.p, m->cand.p,
-                                             m->N, m->conv, m->maxiter, ncand);
+                                             m->N, m->conv, m->maxiter, a.ncand);
   URSM_LAUNCH_CHECK();
   URSM_API_END
 }
@@ -1025,6 +1365,199 @@ int ursm_mle_p2p_error(ursm_mle* mm, int32_t* h_err) {
     URSM_CUDA(cudaMemcpy(h_err, m->p2p->err, sizeof(int), cudaMemcpyDeviceToHost));
     if (*h_err) m->p2p->dirty = true;  // the next fit resets the block behind a barrier
   }
+  URSM_API_END
+}
+
+static size_t p2p_buf_doubles(const Mle* m);
+static double* p2p_buf(const Mle* m, void* base, unsigned long long epoch);
+static unsigned long long* p2p_flags(const Mle* m, void* base);
+
+// One outer iteration of opt_Ak for all columns, enqueued on `st`:
+//   step   (trial steps + decision + installation, and the zeroing the pass needs)
+//   pass   (opt_u + update_gd_coeffConst of the stepped columns -> part_out)
+//   merge  (peer exchange only: part_in <- sum over ranks of the peers' part_out)
+static void mle_enqueue_iteration(Mle* m, int it, cudaStream_t st) {
+  const size_t stride = (size_t)m->K * m->N + m->K;
+  const bool peers = m->p2p != nullptr;
+  const double* part_in;
+  double* part_out;
+  if (peers) {  // epochs advance by kGraphIters (even) per launch from an even base: static parity
+    part_in = m->partbuf.p;
+    part_out = p2p_buf(m, m->p2p->own, (unsigned long long)(it + 1));
+  } else {
+    part_in = m->partbuf.p + (size_t)(it & 1) * stride;
+    part_out = m->partbuf.p + (size_t)((it + 1) & 1) * stride;
+  }
+  const int gslots = (m->N + kGradThreads - 1) / kGradThreads;
+  mle_grad_kernel<<<dim3(gslots, m->K), kGradThreads, 0, st>>>(m->A.p, m->cAinv, m->cA, m->coeffA,
+                                                              part_in, m->act_cur.p, m->N,
+                                                              m->gbuf.p, m->gobj.p);
+  URSM_LAUNCH_CHECK();
+  StepArgs a;
+  memset(&a, 0, sizeof a);
+  a.gbuf = m->gbuf.p;
+  a.gobj = m->gobj.p;
+  a.gslots = gslots;
+  a.Aw = m->A.p;
+  a.zero_out = part_out;
+  a.u_acc = m->ratio.p;
+  a.order = m->sc->order.p;
+  a.type_start = m->type_start.p;
+  a.done = m->done.p;
+  a.act_w = m->act_cur.p;
+  a.niter = m->niter.p;
+  a.halv = m->halv.p;
+  a.base_w = m->base.p;
+  a.delta = m->delta.p;
+  a.lam_store = m->lam_store.p;
+  a.conv = m->conv;
+  a.maxiter = m->maxiter;
+  mle_launch_cand(m, a, part_in, m->act_cur.p, st);
+  mle_pass(m, part_out, st, /*lean=*/true);
+  if (peers) {
+    P2PBlock* b = m->p2p;
+    P2PArgs pa;
+    memset(&pa, 0, sizeof pa);
+    for (int r = 0; r < b->world; ++r) {
+      pa.peer[r] = p2p_buf(m, b->peer[r], (unsigned long long)(it + 1));
+      pa.peer_flags[r] = p2p_flags(m, b->peer[r]);
+    }
+    pa.my_flags = p2p_flags(m, b->own);
+    pa.world = b->world;
+    pa.rank = b->rank;
+    pa.epoch = (unsigned long long)(it + 1);
+    pa.epoch_base = m->epoch_dev.p;
+    pa.err = b->err;
+    mle_p2p_merge_kernel<<<dim3((m->N + 255) / 256, m->K + 1), 256, 0, st>>>(pa, m->partbuf.p,
+                                                                             m->act_cur.p, m->N, m->K);
+    URSM_LAUNCH_CHECK();
+  }
+}
+
+// opt_A_u (:128-154) for the columns flagged in h_active, to completion: the loop of opt_Ak
+// (:157-182) runs on the device -- kGraphIters outer iterations per launch of a captured CUDA
+// graph on the workspace's own stream, three kernels per iteration and no memset; the host only
+// reads the K loop flags back between launches.  With the peer exchange set up
+// (ursm_mle_p2p_open) every rank runs the same graph and the per-iteration sum crosses NVLink
+// inside it.  d_part_init: the all-reduced partials of the pass that preceded the loop.
+// The partials of the last accepted steps are NOT returned: the caller follows up with a full
+// pass (ursm_mle_pass_u), which also refreshes sum_l R_l log u_l.
+int ursm_mle_opt_run(ursm_mle* mm, const int32_t* h_active, double init_step, double conv,
+                     int32_t maxiter, const double* d_part_init, int32_t* h_niter,
+                     int32_t* h_halvings, int32_t* h_launches, void* stream) {
+  URSM_API_BEGIN
+  Mle* m = reinterpret_cast<Mle*>(mm);
+  URSM_REQUIRE(m && m->sc && h_active && d_part_init && m->cAinv && init_step > 0 && maxiter >= 1,
+               "ursm_mle_opt_run: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = m->K;
+  const size_t stride = (size_t)K * m->N + K;
+  const bool peers = m->p2p != nullptr && m->p2p->opened;
+  URSM_REQUIRE(m->p2p == nullptr || peers, "ursm_mle_opt_run: peer exchange allocated but not opened");
+  if (!m->gstream) {
+    URSM_CUDA(cudaStreamCreateWithFlags(&m->gstream, cudaStreamNonBlocking));
+    URSM_CUDA(cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming));
+    URSM_CUDA(cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming));
+    URSM_CUDA(cudaHostAlloc((void**)&m->h_poll, 3 * K * sizeof(int), cudaHostAllocPortable));
+    m->done.alloc(K);
+    m->lam_store.alloc((size_t)K * kCand);
+    m->gbuf.alloc((size_t)K * m->N);
+    m->gobj.alloc((size_t)K * ((m->N + 255) / 256) * 3);
+    m->epoch_dev.alloc(1);
+    URSM_CUDA(cudaDeviceSynchronize());  // pool allocations are ordered on the default stream
+  }
+  if (m->partbuf.n != 2 * stride) {
+    m->partbuf.alloc(2 * stride);
+    URSM_CUDA(cudaDeviceSynchronize());
+  }
+  m->init_step = init_step;
+  m->conv = conv;
+  m->maxiter = maxiter;
+  // everything below runs on the workspace's stream, after what the caller has enqueued
+  URSM_CUDA(cudaEventRecord(m->ev_in, st));
+  URSM_CUDA(cudaStreamWaitEvent(m->gstream, m->ev_in, 0));
+  cudaStream_t g = m->gstream;
+  URSM_CUDA(cudaMemcpyAsync(m->act_cur.p, h_active, K * sizeof(int), cudaMemcpyHostToDevice, g));
+  URSM_CUDA(cudaMemsetAsync(m->niter.p, 0, K * sizeof(int), g));
+  URSM_CUDA(cudaMemsetAsync(m->base.p, 0, K * sizeof(int), g));
+  URSM_CUDA(cudaMemsetAsync(m->halv.p, 0, K * sizeof(int), g));
+  URSM_CUDA(cudaMemsetAsync(m->delta.p, 0, K * sizeof(double), g));
+  URSM_CUDA(cudaMemsetAsync(m->done.p, 0, K * sizeof(int), g));
+  URSM_CUDA(cudaMemsetAsync(m->lam_store.p, 0xFF, (size_t)K * kCand * sizeof(double), g));  // NaN: cold
+  URSM_CUDA(cudaMemcpyAsync(m->partbuf.p, d_part_init, stride * sizeof(double),
+                            cudaMemcpyDeviceToDevice, g));
+  if (peers) {
+    URSM_REQUIRE((m->p2p->epoch & 1ull) == 0, "ursm_mle_opt_run: peer-exchange epoch is odd");
+    URSM_CUDA(cudaMemcpyAsync(m->epoch_dev.p, &m->p2p->epoch, sizeof(unsigned long long),
+                              cudaMemcpyHostToDevice, g));
+  }
+  Mle::GraphKey key;
+  key.init_step = init_step;
+  key.conv = conv;
+  key.maxiter = maxiter;
+  key.ncand = mle_ncand(m);
+  key.p2p = peers ? 1 : 0;
+  key.coeffs = m->cAinv;
+  key.p2p_own = peers ? m->p2p->own : nullptr;
+  key.act = m->act_cur.p;
+  key.cnt = m->sc->cnt.p;
+  key.cnt_w = m->sc->cnt_w;
+  key.sample = m->sc->sample;
+  key.y_smem = mle_cand_y_smem(m);  // (also opts the kernel in to its shared memory, before any capture)
+  if (mle_fused_ok(m)) {  // same for the one-pass kernel
+    int nc;
+    size_t smem;
+    mle_fused_geometry(m, &nc, &smem);
+  }
+  if (!m->gexec || !(m->gkey == key)) {
+    if (m->gexec) {
+      cudaGraphExecDestroy(m->gexec);
+      m->gexec = nullptr;
+    }
+    URSM_CUDA(cudaStreamSynchronize(g));
+    cudaGraph_t graph = nullptr;
+    URSM_CUDA(cudaStreamBeginCapture(g, cudaStreamCaptureModeThreadLocal));
+    try {
+      for (int it = 0; it < kGraphIters; ++it) mle_enqueue_iteration(m, it, g);
+      if (peers) {
+        mle_epoch_bump_kernel<<<1, 1, 0, g>>>(m->epoch_dev.p, (unsigned long long)kGraphIters);
+        URSM_LAUNCH_CHECK();
+      }
+    } catch (...) {
+      cudaStreamEndCapture(g, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    URSM_CUDA(cudaStreamEndCapture(g, &graph));
+    cudaError_t e = cudaGraphInstantiate(&m->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    URSM_CUDA(e);
+    m->gkey = key;
+  }
+  int launches = 0;
+  const int max_launches = (maxiter + kGraphIters - 1) / kGraphIters + 64 + 1024 / mle_ncand(m);
+  while (true) {
+    URSM_CUDA(cudaGraphLaunch(m->gexec, g));
+    count_launch(kGraphIters * (peers ? 5 : 4));
+    ++launches;
+    if (peers) m->p2p->epoch += kGraphIters;
+    URSM_CUDA(cudaMemcpyAsync(m->h_poll, m->act_cur.p, K * sizeof(int), cudaMemcpyDeviceToHost, g));
+    URSM_CUDA(cudaStreamSynchronize(g));
+    bool any = false;
+    for (int k = 0; k < K; ++k) any = any || m->h_poll[k] != 0;
+    if (!any) break;
+    URSM_REQUIRE(launches < max_launches, "ursm_mle_opt_run: the opt_Ak loop did not terminate");
+  }
+  URSM_CUDA(cudaMemcpyAsync(m->h_poll + K, m->niter.p, K * sizeof(int), cudaMemcpyDeviceToHost, g));
+  URSM_CUDA(cudaMemcpyAsync(m->h_poll + 2 * K, m->halv.p, K * sizeof(int), cudaMemcpyDeviceToHost, g));
+  URSM_CUDA(cudaStreamSynchronize(g));
+  for (int k = 0; k < K; ++k) {
+    if (h_niter) h_niter[k] = m->h_poll[K + k];
+    if (h_halvings) h_halvings[k] = m->h_poll[2 * K + k];
+  }
+  if (h_launches) *h_launches = launches;
+  URSM_CUDA(cudaEventRecord(m->ev_out, g));
+  URSM_CUDA(cudaStreamWaitEvent(st, m->ev_out, 0));
   URSM_API_END
 }
 

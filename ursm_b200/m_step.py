@@ -213,18 +213,32 @@ class LogitNormalMLE(object):
         self._refresh_host_coeffs()
 
     def _refresh_host_coeffs(self):
-        """Host mirrors of the reference's attributes (N x K), for inspection/tests."""
-        K, N, KN = self.K, self.N, self.K * self.N
-        t = lambda x: np.ascontiguousarray(x.cpu().numpy().reshape(K, N).T)
-        self.gd_coeffAinv = t(self._cAinv)
-        self.gd_coeffA = t(self._cA)
-        if self.hasSC:
-            self.gd_coeffConst = t(self._coeffA - self._part[:KN])
-            u = np.empty(self._owners[0].L)
-            _lib.call("ursm_mle_get_u", self._h, _lib.ptr(u))
-            self.u = u
-        else:
-            self.gd_coeffConst = np.zeros((N, K))
+        """The reference's attributes `gd_coeffAinv`, `gd_coeffA`, `gd_coeffConst` (N x K) and
+        `u` (L) mirror device buffers; they are pulled when somebody reads them (tests,
+        inspection), not on every update -- the EM loop itself never needs them."""
+        self._host_cache = {}
+
+    def _host(self, name):
+        c = self.__dict__.setdefault("_host_cache", {})
+        if name not in c:
+            K, N, KN = self.K, self.N, self.K * self.N
+            t = lambda x: np.ascontiguousarray(x.cpu().numpy().reshape(K, N).T)
+            if name == "gd_coeffAinv":
+                c[name] = t(self._cAinv)
+            elif name == "gd_coeffA":
+                c[name] = t(self._cA)
+            elif name == "gd_coeffConst":
+                c[name] = t(self._coeffA - self._part[:KN]) if self.hasSC else np.zeros((N, K))
+            elif name == "u":
+                u = np.empty(self._owners[0].L)
+                _lib.call("ursm_mle_get_u", self._h, _lib.ptr(u))
+                c[name] = u
+        return c[name]
+
+    gd_coeffAinv = property(lambda self: self._host("gd_coeffAinv"))
+    gd_coeffA = property(lambda self: self._host("gd_coeffA"))
+    gd_coeffConst = property(lambda self: self._host("gd_coeffConst"))
+    u = property(lambda self: self._host("u"))
 
     def opt_kappa_tau(self):
         """m_step.py:92-103 (closed form; global sums came through the all-reduce)."""
@@ -261,44 +275,54 @@ class LogitNormalMLE(object):
                           _lib.stream_ptr())
                 logging.debug("\t\tOptimized A%d with closed form solution", k)
         self.niter_A[:] = 0
+        self.graph_launches = 0
         if active.any():
             st = _lib.stream_ptr()
-            _lib.call("ursm_mle_opt_begin", self._h, _lib.ptr(active), float(init_step),
-                      float(self.MLE_CONV), int(self.MLE_maxiter), st)
             multi = dist.world_size() > 1
             niter = np.zeros(K, dtype=np.int32)
             halv = np.zeros(K, dtype=np.int32)
-            it, poll_every = 0, 8
-            while True:
-                _lib.call("ursm_mle_opt_step", self._h, self._p(self._part), st)
+            if self._p2p or not multi:
+                # the whole loop on the device: a captured graph of 16 outer iterations per
+                # launch (step + decision + installation, then the opt_u / coeffConst pass; with
+                # peers, the N*K + K values per iteration of SURVEY 8e are summed over NVLink
+                # peer memory inside the same graph -- no collective call)
+                nl = ctypes.c_int32(0)
+                _lib.call("ursm_mle_opt_run", self._h, _lib.ptr(active), float(init_step),
+                          float(self.MLE_CONV), int(self.MLE_maxiter), self._p(self._part),
+                          _lib.ptr(niter), _lib.ptr(halv), ctypes.byref(nl), st)
+                self.graph_launches = int(nl.value)
                 if self._p2p:
-                    # N*K + K values per outer iteration, summed over NVLink peer
-                    # memory inside the merge kernel -- no collective call
-                    _lib.call("ursm_mle_opt_pass_p2p", self._h, st)
-                    _lib.call("ursm_mle_opt_merge_p2p", self._h, self._p(self._part), st)
-                else:
+                    err = ctypes.c_int32(0)
+                    _lib.call("ursm_mle_p2p_error", self._h, ctypes.byref(err))
+                    if err.value:
+                        raise _lib.UrsmError("M-step peer exchange: a rank did not reach the "
+                                             "iteration barrier (timeout)")
+            else:
+                # several ranks without the peer exchange (URSM_MLE_P2P=0, gloo, > 16 ranks): one
+                # NCCL all-reduce per outer iteration, flags polled every `poll_every` iterations
+                _lib.call("ursm_mle_opt_begin", self._h, _lib.ptr(active), float(init_step),
+                          float(self.MLE_CONV), int(self.MLE_maxiter), st)
+                it, poll_every = 0, 8
+                while True:
+                    _lib.call("ursm_mle_opt_step", self._h, self._p(self._part), st)
                     _lib.call("ursm_mle_opt_pass", self._h, self._p(self._part_local), st)
-                    if multi:
-                        dist.all_reduce_(self._part_local)
+                    dist.all_reduce_(self._part_local)
                     _lib.call("ursm_mle_opt_merge", self._h, self._p(self._part_local),
                               self._p(self._part), st)
-                it += 1
-                if it % poll_every == 0:
-                    _lib.call("ursm_mle_opt_poll", self._h, _lib.ptr(active), _lib.ptr(niter),
-                              _lib.ptr(halv), None, st)
-                    if not active.any():
-                        break
-            if self._p2p:
-                err = ctypes.c_int32(0)
-                _lib.call("ursm_mle_p2p_error", self._h, ctypes.byref(err))
-                if err.value:
-                    raise _lib.UrsmError("M-step peer exchange: a rank did not reach the "
-                                         "iteration barrier (timeout)")
+                    it += 1
+                    if it % poll_every == 0:
+                        _lib.call("ursm_mle_opt_poll", self._h, _lib.ptr(active), _lib.ptr(niter),
+                                  _lib.ptr(halv), None, st)
+                        if not active.any():
+                            break
             self.niter_A[:] = niter
             self.nhalvings += int(halv.sum())
             for k in range(K):
                 if niter[k] > 0:
                     logging.debug("\t\tOptimized A%d in %d iterations", k, niter[k])
+            # u, gd_coeffConst and sum_l R_l log u_l of the final columns (the loop leaves the
+            # partials of columns that stopped early behind)
+            self._pass_u(self._has_cells)
         self._pull_A()
         self._refresh_host_coeffs()
 
