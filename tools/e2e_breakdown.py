@@ -27,7 +27,12 @@ def main():
     args = ap.parse_args()
     cfg = bench.WORKLOADS[args.workload]
     K, N, L, M = cfg["K"], cfg["N"], cfg["L"], cfg["M"]
-    torch.cuda.set_device(0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:  # torchrun: every rank keeps its block of the rows (sharded fit)
+        import torch.distributed as td
+        td.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     A_true = synth.profile_matrix(N, K, seed=0)
     G = (np.arange(L) % K).astype(np.int64) if L else None
     hY = hX = None
@@ -90,6 +95,8 @@ def main():
     times = []
     for _ in range(args.reps):
         step(times)
+    if local != 0:
+        sys.stdout = open(os.devnull, "w")
     names = ["ctor(init_para)", "init_gibbs(upload)", "init_mle", "estep", "suffstats+elbo+alpha",
              "opt_A_u+elbo", "gathered_stats(d2h)", "destroy"]
     tm = np.median(np.array(times), axis=0) * 1e3

@@ -37,6 +37,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <type_traits>
 
 namespace ursm {
 
@@ -71,7 +72,14 @@ struct ScGibbsArgs {
   double* kt_out;           // [2][L]
   int* rounds_out;          // [L]
   int dump_all;             // w_out / S_out / kt_out hold EVERY sweep ([nsweeps][...]), not the last
+  unsigned char* state;     // BIG variant: [grid][slots] x (w fp32 | threshold fp32 | counter u16)
 };
+
+// bit masks over a thread's run of genes: 32 bits, or 64 in the BIG variant
+__device__ __forceinline__ int mask_ffs(unsigned int m) { return __ffs((int)m); }
+__device__ __forceinline__ int mask_ffs(unsigned long long m) { return __ffsll((long long)m); }
+__device__ __forceinline__ int mask_popc(unsigned int m) { return __popc(m); }
+__device__ __forceinline__ int mask_popc(unsigned long long m) { return __popcll(m); }
 
 // acc[slot] += (dA, dQ).  Shared memory or an L1-cached scratch row: plain 8-byte
 // read-modify-write (one lane per slot at a time).  L2-resident scratch row and no L1 to
@@ -110,8 +118,13 @@ __device__ __forceinline__ int slot_of_gene(int i, int g, int T, float inv_g) {
 
 constexpr int kNormChunk = 64;  // (kappa, tau) normal pairs precomputed per refill
 
-template <bool ACC_SMEM>
+// BIG: gene vectors whose chain state (10 B per gene) does not fit in shared memory (N > ~22,700)
+// keep w, the thresholds and the counters in a CTA-private, L2-resident scratch row instead, and
+// a thread owns up to 64 genes (64-bit masks): any N <= 65,536.  Same code otherwise.
+template <bool ACC_SMEM, bool BIG>
 __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
+  using MT = typename std::conditional<BIG, unsigned long long, unsigned int>::type;
+  constexpr int kMaskBits = BIG ? 64 : 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = a.g, N = a.N, slots = a.slots, nw = T >> 5;
@@ -124,14 +137,18 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
   double* bc = nrm + 2 * kNormChunk;                          // [4] broadcast
   int* redN = reinterpret_cast<int*>(bc + 4);                 // [2][32] scan: warp counts of S
   int* ibc = redN + 64;                                       // [4]
-  float* w_s = reinterpret_cast<float*>(ibc + 4);             // [slots] w of the current sweep
+  unsigned char* st_base = BIG ? a.state + (size_t)blockIdx.x * slots * 10
+                               : reinterpret_cast<unsigned char*>(ibc + 4);
+  float* w_s = reinterpret_cast<float*>(st_base);             // [slots] w of the current sweep
   float* T_s = w_s + slots;                                   // [slots] draw_S thresholds
   // coeffA / coeffAsq partials of gene slot s: acc[s] = (dA, dQ), one 8-byte access
   float2* acc = reinterpret_cast<float2*>(ACC_SMEM ? (T_s + slots)
                                                    : (a.scratch + (size_t)blockIdx.x * 2 * slots));
-  unsigned int* Sm_s =
-      reinterpret_cast<unsigned int*>(ACC_SMEM ? (T_s + 3 * (size_t)slots) : (T_s + slots));  // [T]
-  unsigned short* cnt_s = reinterpret_cast<unsigned short*>(Sm_s + T);                       // [slots]
+  MT* Sm_s = reinterpret_cast<MT*>(
+      BIG ? reinterpret_cast<unsigned char*>(ibc + 4)
+          : reinterpret_cast<unsigned char*>(ACC_SMEM ? (T_s + 3 * (size_t)slots) : (T_s + slots)));  // [T]
+  unsigned short* cnt_s = BIG ? reinterpret_cast<unsigned short*>(T_s + slots)
+                              : reinterpret_cast<unsigned short*>(Sm_s + T);                 // [slots]
 
   const double inv_sample = 1.0 / (double)a.sample;
   double* coeffA = a.stats;
@@ -141,7 +158,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
   // this thread's run (phase 2): genes i0 .. i0 + gcount - 1, bit j of the masks below
   const int i0 = tid * g;
   const int gcount = max(0, min(g, N - i0));
-  const unsigned int validm = gcount >= 32 ? 0xffffffffu : ((1u << gcount) - 1u);
+  const MT validm = gcount >= kMaskBits ? ~(MT)0 : (((MT)1 << gcount) - (MT)1);
   // this warp's queue (phase 1): entry e -> owner thread wfirst + (e & 31), gene j = e >> 5
   const int wfirst = tid & ~31;
   const int qtotal = (wfirst * g < N) ? 32 * g : 0;
@@ -189,13 +206,13 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       cnt_s[slot] = 0;
     }
     __syncthreads();
-    unsigned int posm = 0u, Sm = 0u;
+    MT posm = 0, Sm = 0;
     for (int j = 0; j < gcount; ++j) {
       const int i = i0 + j;
-      const unsigned int pos = w_s[j * T + tid] > 0.f ? 1u : 0u;
-      unsigned int S;
+      const MT pos = w_s[j * T + tid] > 0.f ? 1 : 0;
+      MT S;
       if (a.S0) {
-        S = a.S0[(size_t)l * N + i] ? 1u : 0u;
+        S = a.S0[(size_t)l * N + i] ? 1 : 0;
       } else {
         Philox r0(a.key, (uint32_t)i, gl, kPurposeInit);
         S = r0.next() >> 31;
@@ -203,14 +220,14 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       posm |= pos << j;
       Sm |= (S | pos) << j;
     }
-    const unsigned int zerom = validm & ~posm;  // genes the draw_S scan visits
+    const MT zerom = validm & ~posm;  // genes the draw_S scan visits
     Sm_s[tid] = Sm;
     double kappa = a.kt0 ? a.kt0[l] : a.mu_k;
     double tau = a.kt0 ? a.kt0[a.L + l] : a.mu_t;
     double s_cur;
     {
       double part = 0.0;
-      for (unsigned int m = Sm; m; m &= m - 1u) part += (double)Acol[(__ffs(m) - 1) * T + tid];
+      for (MT m = Sm; m; m &= m - 1) part += (double)Acol[(mask_ffs(m) - 1) * T + tid];
       s_cur = block_sum(part, red);  // (its barriers also order the staging reads above)
     }
 
@@ -259,7 +276,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
                 slot = j * T + to;
                 av = Acol[slot];
                 if (prev_ret) {  // update_suffStats (:245-270) of the previous sweep
-                  const unsigned int Sp = (Sm_s[to] >> j) & 1u;
+                  const unsigned int Sp = (unsigned int)((Sm_s[to] >> j) & 1);
                   const float wold = w_s[slot];
                   const float dA = ((float)Sp - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
                   acc_add<ACC_SMEM>(acc + slot, dA, dQ, a.acc_red);
@@ -313,7 +330,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       // are in shared memory, so a re-scan is a handful of flops per zero gene), to the
       // fixed point.  S lives in a register bit mask per owner thread.
       double s_run = s_cur, used_in = s_cur, total = 0.0;
-      unsigned int Snew_m = Sm;
+      MT Snew_m = Sm;
       float margin = INFINITY;
       bool scan = true;
       int rounds = 0;
@@ -322,15 +339,15 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
           margin = INFINITY;
           s_run = used_in;
           Snew_m = Sm;
-          for (unsigned int m = zerom; m; m &= m - 1u) {
-            const int j = __ffs(m) - 1;
+          for (MT m = zerom; m; m &= m - 1) {
+            const int j = mask_ffs(m) - 1;
             const double ad = (double)Acol[j * T + tid];
             const double Tth = (double)T_s[j * T + tid];
-            const double so = s_run - (((Sm >> j) & 1u) ? ad : 0.0);
+            const double so = s_run - (((Sm >> j) & 1) ? ad : 0.0);
             const bool on = so > Tth;
             margin = fminf(margin, fabsf((float)(so - Tth)));
             s_run = so + (on ? ad : 0.0);
-            Snew_m = on ? (Snew_m | (1u << j)) : (Snew_m & ~(1u << j));
+            Snew_m = on ? (Snew_m | ((MT)1 << j)) : (Snew_m & ~((MT)1 << j));
           }
         }
         // block-wide exclusive scan of the net changes (double-buffered warp totals)
@@ -342,7 +359,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
           if (lane >= o) inc += t;
         }
         const int buf = (rounds & 1) * 32;
-        const int nSw = __reduce_add_sync(0xffffffffu, __popc(Snew_m & validm));
+        const int nSw = __reduce_add_sync(0xffffffffu, mask_popc(Snew_m & validm));
         if (lane == 31) redA[buf + warp] = inc;
         if (lane == 0) redN[buf + warp] = nSw;
         __syncthreads();
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
         for (int i = tid; i < N; i += T) {
           const int slot = slot_of_gene(i, g, T, inv_g);
           a.w_out[base + i] = w_s[slot];
-          a.S_out[base + i] = (Sm_s[slot % T] >> (slot / T)) & 1u;
+          a.S_out[base + i] = (unsigned char)((Sm_s[slot % T] >> (slot / T)) & 1);
         }
         if (tid == 0) {
           a.kt_out[sw_i * 2 * a.L + l] = kappa;
@@ -430,7 +447,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       const float cA1 = pt, cA2 = pt * pk, cQ = -0.5f * pt * pt;
       for (int j = 0; j < gcount; ++j) {
         const int slot = j * T + tid;
-        const unsigned int Sold = (Sm >> j) & 1u;
+        const unsigned int Sold = (unsigned int)((Sm >> j) & 1);
         const float wold = w_s[slot];
         const float dA = ((float)Sold - 0.5f) * cA1 - wold * cA2, dQ = cQ * wold;
         acc_add<ACC_SMEM>(acc + slot, dA, dQ, a.acc_red);
@@ -447,7 +464,7 @@ __global__ void __launch_bounds__(1024, 1) sc_gibbs_kernel(ScGibbsArgs a) {
       if (a.w_out && !a.dump_all) a.w_out[(size_t)l * N + i] = w_s[slot];
       if (a.S_out && !a.dump_all) {
         const int to = slot % T, j = slot / T;
-        a.S_out[(size_t)l * N + i] = (Sm_s[to] >> j) & 1u;
+        a.S_out[(size_t)l * N + i] = (unsigned char)((Sm_s[to] >> j) & 1);
       }
     }
     if (tid == 0) {
@@ -639,6 +656,11 @@ static size_t sc_smem_bytes(int T, int g, bool acc_smem) {
   const size_t fixed = (32 + 64 + 96 + 2 * kNormChunk + 4) * 8 + (64 + 4) * 4 + (size_t)T * 4;
   return fixed + (size_t)T * g * (acc_smem ? 18 : 10) + 16;
 }
+// BIG variant: the per-gene state lives in global scratch; shared memory holds the fixed part
+// and one 64-bit S mask per thread
+static size_t sc_smem_bytes_big(int T) {
+  return (32 + 64 + 96 + 2 * kNormChunk + 4) * 8 + (64 + 4) * 4 + (size_t)T * 8 + 16;
+}
 
 // Geometry: the kernel is bound by dependent-instruction latency, not by instruction
 // count, so what matters is resident warps per SM (64 registers per thread and the
@@ -655,12 +677,14 @@ static void sc_pick_geometry(ScShard* s) {
   if (const char* e = getenv("URSM_SC_ACC_SMEM_LIMIT")) acc_limit = atoi(e);
   int g_lo = 8, g_hi = 32;
   if (const char* e = getenv("URSM_SC_GENES_PER_THREAD")) g_lo = g_hi = std::max(1, std::min(32, atoi(e)));
-  URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem_optin));
-  URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem_optin));
+  URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<true, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin));
+  URSM_CUDA(cudaFuncSetAttribute(sc_gibbs_kernel<false, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin));
   double best = -1.0;
-  for (int gpt = g_lo; gpt <= g_hi; ++gpt) {
+  bool force_big = false;
+  if (const char* e = getenv("URSM_SC_STATE_GLOBAL")) force_big = atoi(e) != 0;  // tests
+  for (int gpt = g_lo; gpt <= g_hi && !force_big; ++gpt) {
     int T = ((s->N + gpt - 1) / gpt + 31) / 32 * 32;
     T = std::max(64, std::min(maxT, T));
     const int g = (s->N + T - 1) / T;
@@ -670,9 +694,11 @@ static void sc_pick_geometry(ScShard* s) {
     if (smem > smem_optin) continue;
     int occ = 0;
     if (acc) {
-      URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<true>, T, smem));
+      URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<true, false>, T,
+                                                              smem));
     } else {
-      URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<false>, T, smem));
+      URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<false, false>, T,
+                                                              smem));
     }
     if (occ < 1) continue;
     const double score = (double)occ * (T / 32) * ((double)s->N / ((double)T * g));
@@ -685,14 +711,32 @@ static void sc_pick_geometry(ScShard* s) {
       s->occ = occ;
     }
   }
-  URSM_REQUIRE(best > 0.0, "gene count too large for the chain-resident single-cell kernel "
-                           "(10 bytes of shared memory per gene, at most 32 genes per thread)");
+  s->big = false;
+  if (best <= 0.0) {
+    // the chain state of a cell (10 B per gene) does not fit in shared memory: keep it in a
+    // CTA-private scratch row in global memory (L2-resident) and let a thread own up to 64 genes
+    int T = ((s->N + g_hi - 1) / g_hi + 31) / 32 * 32;  // same genes-per-thread target as above
+    T = std::max(64, std::min(maxT, T));
+    const int g = (s->N + T - 1) / T;
+    URSM_REQUIRE(g <= 64, "gene count too large for the single-cell kernel (at most 65,536 genes)");
+    s->T = T;
+    s->g = g;
+    s->acc_smem = false;
+    s->smem = (int)sc_smem_bytes_big(T);
+    s->big = true;
+    int occ = 0;
+    URSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sc_gibbs_kernel<false, true>, T,
+                                                            (size_t)s->smem));
+    URSM_REQUIRE(occ >= 1, "single-cell kernel (large gene vectors): no resident CTA fits");
+    s->occ = occ;
+  }
   s->slots = s->T * s->g;
   long long want = (long long)s->num_sms * s->occ;
   if (const char* e = getenv("URSM_SC_GRID"))  // tests: many cells (and type changes) per CTA
     want = std::max(1, atoi(e));
   s->grid = (int)std::max<long long>(1, std::min<long long>(want, s->L));
   if (!s->acc_smem) s->scratch.alloc((size_t)s->grid * 2 * s->slots);
+  if (s->big) s->state.alloc((size_t)s->grid * s->slots * 10);
 }
 
 static void sc_finish_create(ScShard* s, const int64_t* h_G) {
@@ -748,7 +792,7 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
   a.flush_every = 16;
   a.counter = s->counter.p;
   URSM_CUDA(cudaMemsetAsync(s->counter.p, 0, sizeof(int), st));
-  a.acc_red = (!s->acc_smem && s->smem > 128 * 1024) ? 1 : 0;
+  a.acc_red = (!s->acc_smem && (s->smem > 128 * 1024 || s->big)) ? 1 : 0;
   if (const char* e = getenv("URSM_SC_ACC_RED"))  // tests: the reduction path on small inputs
     a.acc_red = (!s->acc_smem && atoi(e)) ? 1 : 0;
   if (!s->ev0) {
@@ -756,10 +800,13 @@ static void sc_launch(ScShard* s, ScGibbsArgs& a, cudaStream_t st) {
     URSM_CUDA(cudaEventCreate(&s->ev1));
   }
   URSM_CUDA(cudaEventRecord(s->ev0, st));
-  if (s->acc_smem)
-    sc_gibbs_kernel<true><<<s->grid, s->T, s->smem, st>>>(a);
+  a.state = s->state.p;
+  if (s->big)
+    sc_gibbs_kernel<false, true><<<s->grid, s->T, s->smem, st>>>(a);
+  else if (s->acc_smem)
+    sc_gibbs_kernel<true, false><<<s->grid, s->T, s->smem, st>>>(a);
   else
-    sc_gibbs_kernel<false><<<s->grid, s->T, s->smem, st>>>(a);
+    sc_gibbs_kernel<false, false><<<s->grid, s->T, s->smem, st>>>(a);
   URSM_LAUNCH_CHECK();
   URSM_CUDA(cudaEventRecord(s->ev1, st));
   s->timed = true;
@@ -834,7 +881,7 @@ int ursm_sc_geometry(const ursm_sc* sc, int32_t* threads, int32_t* genes_per_thr
   if (genes_per_thread) *genes_per_thread = s->g;
   if (grid) *grid = s->grid;
   if (smem_bytes) *smem_bytes = s->smem;
-  if (acc_in_smem) *acc_in_smem = s->acc_smem ? 1 : 0;
+  if (acc_in_smem) *acc_in_smem = s->big ? -1 : (s->acc_smem ? 1 : 0);  // -1: state in global scratch
   return 0;
 }
 

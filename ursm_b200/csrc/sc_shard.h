@@ -23,6 +23,7 @@ struct ScShard {
     if (cnt_w == width) return;
     cnt.alloc((size_t)L * N * width);
     cnt.zero();
+    cudaStreamSynchronize(0);  // allocation and zeroing are ordered on the default stream only
     cnt_w = width;
   }
   DevBuf<double> cellmom;        // [4][L] E kappa, E tau, E kappa^2, E tau^2
@@ -31,7 +32,8 @@ struct ScShard {
   DevBuf<float> Aslot;           // [K][slots] fp32 copy of A^T in the Gibbs kernel's slot order
   DevBuf<float> scratch;         // [grid][slots][2] CTA-private accumulators (L2-resident)
   int T = 0, g = 0, slots = 0, smem = 0, occ = 0, grid = 0, num_sms = 0;
-  bool acc_smem = false, has_params = false;
+  DevBuf<unsigned char> state;   // BIG variant: [grid][slots] x 10 B chain state (w, threshold, counter)
+  bool acc_smem = false, has_params = false, big = false;
   double pkappa[2] = {0, 1}, ptau[2] = {0, 1};
   int sample = 1;                // divisor that turns cnt into E[S]
   std::vector<long long> type_count, type_start;  // cells per type; offsets into `order`

@@ -21,6 +21,7 @@ Differences that a caller can observe (all deliberate):
 """
 import ctypes
 import logging
+import weakref
 
 import numpy as np
 
@@ -29,19 +30,65 @@ from . import _lib, dist
 _DEFAULT_SEED = 20171106
 
 
+class _on_side_stream(object):
+    """Context: enqueue on the sampler's own (non-blocking) stream, ordered after everything
+    already enqueued on the caller's stream."""
+
+    def __init__(self, sampler):
+        self.sampler = sampler
+
+    def __enter__(self):
+        torch = self.sampler._torch
+        if self.sampler._stream is None:
+            self.sampler._stream = torch.cuda.Stream()
+        self.sampler._stream.wait_stream(torch.cuda.current_stream())
+        self.ctx = torch.cuda.stream(self.sampler._stream)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+
+def _join_side_stream(sampler):
+    """The caller's stream waits for what the sampler has enqueued on its own."""
+    if sampler._stream is not None:
+        sampler._torch.cuda.current_stream().wait_stream(sampler._stream)
+
+
+class _Shard(object):
+    """Owner of a device shard handle (ursm_sc / ursm_bk): destroyed when the last Python
+    object that needs the device data is gone.  The sampler and the lazy `exp_S` view both hold
+    one, so a `suff_stats` dict stays readable after its sampler has been dropped (the
+    reference's dicts are plain host arrays) without a sampler <-> dict reference cycle."""
+
+    def __init__(self, h, destroy):
+        self.h, self._destroy = h, destroy
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                getattr(_lib.load(), self._destroy)(h)
+            except Exception:
+                pass
+
+
 class DeviceExpS(object):
     """`suff_stats["exp_S"]` (L x N, e_step_gibbs.py:232,247): a lazy view of the
     8- or 16-bit counters that stay on the device (local shard rows)."""
 
     def __init__(self, sampler):
-        self._sampler = sampler
+        # the shard handle, not the sampler: the sampler owns the dict this object sits in, and
+        # a reference back to it would leave whole device shards to the garbage collector
+        self._shard = sampler._shard
         self.shape = (sampler.L, sampler.N)
         self.dtype = np.dtype(np.float64)
         self.ndim = 2
 
     def rows(self, lo, hi):
         out = _lib.host_result((hi - lo, self.shape[1]))
-        _lib.call("ursm_sc_get_exp_S", self._sampler._h, _lib.ptr(out), int(lo), int(hi - lo))
+        _lib.call("ursm_sc_get_exp_S", self._shard.h, _lib.ptr(out), int(lo), int(hi - lo))
         return out
 
     def __array__(self, dtype=None, copy=None):
@@ -92,12 +139,25 @@ class LogitNormalGibbs_SC(object):
             Y = _lib.f64(SCexpr)
             _lib.call("ursm_sc_create", ctypes.byref(h), _lib.ptr(Y), _lib.ptr(Gi), self.L,
                       self.N, self.K, self.row_offset)
-        self._h = h
+        self._shard = _Shard(h, "ursm_sc_destroy")
         n = _lib.load().ursm_sc_stats_len(h)
         self._stats = torch.zeros(n, dtype=torch.float64, device="cuda")
         if self.A is not None:
             self._push_params()
-        self.suff_stats = {}
+        self._suff, self._pending, self._stream = {}, False, None
+
+    # `gibbs()` only ENQUEUES the E-step (on this sampler's own stream, so that the single-cell
+    # and the bulk E-step of an EM iteration can share the machine); the statistics are
+    # all-reduced and read back when `suff_stats` is first looked at.
+    @property
+    def suff_stats(self):
+        if self._pending:
+            self._publish()
+        return self._suff
+
+    @suff_stats.setter
+    def suff_stats(self, value):
+        self._suff, self._pending = value, False
 
     def type_sums(self):
         """K x N: per type, the sum over this shard's cells of the row-normalised counts
@@ -106,13 +166,9 @@ class LogitNormalGibbs_SC(object):
         _lib.call("ursm_sc_type_sums", self._h, ctypes.c_void_p(out.data_ptr()), _lib.stream_ptr())
         return out.cpu().numpy().reshape(self.K, self.N)
 
-    def __del__(self):
-        h, self._h = getattr(self, "_h", None), None
-        if h:
-            try:
-                _lib.load().ursm_sc_destroy(h)
-            except Exception:
-                pass
+    @property
+    def _h(self):
+        return self._shard.h
 
     # -- reference API ---------------------------------------------------
     def init_gibbs(self):
@@ -130,11 +186,12 @@ class LogitNormalGibbs_SC(object):
         """e_step_gibbs.py:286-304: restart the chain, `burnin` + `sample*thin`
         cycles, statistics from every `thin`-th retained cycle."""
         logging.debug("\tE-step for single cells started.")
-        _lib.call("ursm_sc_gibbs", self._h, int(burnin), int(sample), int(thin),
-                  ctypes.c_uint64(self.seed), ctypes.c_uint64(self.em_iter),
-                  ctypes.c_void_p(self._stats.data_ptr()), _lib.stream_ptr())
+        with _on_side_stream(self):
+            _lib.call("ursm_sc_gibbs", self._h, int(burnin), int(sample), int(thin),
+                      ctypes.c_uint64(self.seed), ctypes.c_uint64(self.em_iter),
+                      ctypes.c_void_p(self._stats.data_ptr()), _lib.stream_ptr())
         self.em_iter += 1
-        self._publish()
+        self._pending = True
 
     # -- parity hooks ----------------------------------------------------
     def inject(self, w, S, kappa, tau, sample, reset=False):
@@ -200,6 +257,8 @@ class LogitNormalGibbs_SC(object):
     def _publish(self):
         """All-reduce the packed statistics and expose them under the reference's keys."""
         N, K, L = self.N, self.K, self.L
+        self._pending = False
+        _join_side_stream(self)
         dist.all_reduce_(self._stats)  # the ONE collective of the single-cell E-step
         host = self._stats.cpu().numpy()
         mom = [np.empty(L) for _ in range(4)]
@@ -217,9 +276,9 @@ class LogitNormalGibbs_SC(object):
             raise _lib.UrsmError("single-cell Gibbs kernel: the draw_S scan did not reach its "
                                  "fixed point for %d (cell, sweep) pairs" % int(host[2 * N * K + 5]))
         # hidden hand-over to LogitNormalMLE: device buffers + global scalar sums
-        st["_ursm_sc"] = self
+        st["_ursm_sc"] = weakref.ref(self)
         st["_ursm_sc_sums"] = host[2 * N * K + 1:2 * N * K + 5].copy()  # sum k, k^2, t, t^2
-        self.suff_stats = st
+        self._suff = st
 
 
 class LogitNormalGibbs_BK(object):
@@ -250,12 +309,23 @@ class LogitNormalGibbs_BK(object):
             X = _lib.f64(BKexpr)
             _lib.call("ursm_bk_create", ctypes.byref(h), _lib.ptr(X), self.M, self.N, self.K,
                       self.row_offset)
-        self._h = h
+        self._shard = _Shard(h, "ursm_bk_destroy")
         n = _lib.load().ursm_bk_stats_len(h)
         self._stats = torch.zeros(n, dtype=torch.float64, device="cuda")
         if self.A is not None:
             self._push_params()
-        self.suff_stats = {}
+        self._suff, self._pending, self._stream = {}, False, None
+
+    @property
+    def suff_stats(self):
+        """See LogitNormalGibbs_SC.suff_stats: materialised on first access after `gibbs()`."""
+        if self._pending:
+            self._publish()
+        return self._suff
+
+    @suff_stats.setter
+    def suff_stats(self, value):
+        self._suff, self._pending = value, False
 
     def profile_sum(self):
         """N-vector: the sum over this shard's bulk samples of the row-normalised counts
@@ -265,13 +335,9 @@ class LogitNormalGibbs_BK(object):
                   _lib.stream_ptr())
         return out.cpu().numpy()
 
-    def __del__(self):
-        h, self._h = getattr(self, "_h", None), None
-        if h:
-            try:
-                _lib.load().ursm_bk_destroy(h)
-            except Exception:
-                pass
+    @property
+    def _h(self):
+        return self._shard.h
 
     def init_gibbs(self):
         """e_step_gibbs.py:39-55: W = 1/K, or seeded from the marker genes (needs the
@@ -310,16 +376,17 @@ class LogitNormalGibbs_BK(object):
     def gibbs(self, burnin=100, sample=100, thin=1, mean_approx=True):
         """e_step_gibbs.py:90-117."""
         sp = ctypes.c_void_p(self._stats.data_ptr())
-        if mean_approx:
-            logging.debug("\tE-step (one-step mean-update) for bulk samples started.")
-            _lib.call("ursm_bk_mean_step", self._h, sp, _lib.stream_ptr())
-        else:
-            logging.debug("\tE-step for bulk samples started.")
-            _lib.call("ursm_bk_gibbs", self._h, int(burnin), int(sample), int(thin),
-                      ctypes.c_uint64(self.seed), ctypes.c_uint64(self.em_iter), int(self.freeze),
-                      sp, _lib.stream_ptr())
+        with _on_side_stream(self):
+            if mean_approx:
+                logging.debug("\tE-step (one-step mean-update) for bulk samples started.")
+                _lib.call("ursm_bk_mean_step", self._h, sp, _lib.stream_ptr())
+            else:
+                logging.debug("\tE-step for bulk samples started.")
+                _lib.call("ursm_bk_gibbs", self._h, int(burnin), int(sample), int(thin),
+                          ctypes.c_uint64(self.seed), ctypes.c_uint64(self.em_iter),
+                          int(self.freeze), sp, _lib.stream_ptr())
         self.em_iter += 1
-        self._publish()
+        self._pending = True
 
     def kernel_ms(self):
         """Device time of the last bulk E-step's kernels."""
@@ -333,6 +400,8 @@ class LogitNormalGibbs_BK(object):
 
     def _publish(self):
         N, K, M = self.N, self.K, self.M
+        self._pending = False
+        _join_side_stream(self)
         dist.all_reduce_(self._stats)  # the ONE collective of the bulk E-step
         host = self._stats.cpu().numpy()
         eZjk, eLogW, eW = np.empty((M, K)), np.empty((K, M)), np.empty((K, M))
@@ -343,6 +412,6 @@ class LogitNormalGibbs_BK(object):
         st["exp_Zjk"] = eZjk
         st["exp_logW"] = eLogW
         st["exp_W"] = eW
-        st["_ursm_bk"] = self
+        st["_ursm_bk"] = weakref.ref(self)
         st["_ursm_bk_tail"] = host[N * K:N * K + K + 1].copy()  # sum_j E log W_k | sum Zjk*logW
-        self.suff_stats = st
+        self._suff = st

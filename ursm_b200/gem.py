@@ -216,15 +216,22 @@ class LogitNormalGEM(object):
     # EM (gem.py:135-195)
     # ------------------------------------------------------------------
     def estep_gibbs(self):
+        """gem.py:135-149.  Both samplers only enqueue their kernels (each on its own stream:
+        the bulk sweeps fill the SMs the persistent single-cell kernel leaves idle in its
+        tail); the statistics are collected afterwards."""
         self.suff_stats = {}
         if self.hasSC:
             self.Gibbs_SC.update_parameters(self.A, self.pkappa, self.ptau)
-            self.Gibbs_SC.gibbs(burnin=self.burnin, sample=self.sample, thin=self.thin)
-            self.suff_stats.update(self.Gibbs_SC.suff_stats)
         if self.hasBK:
             self.Gibbs_BK.update_parameters(self.A, self.alpha)
+        if self.hasSC:
+            self.Gibbs_SC.gibbs(burnin=self.burnin, sample=self.sample, thin=self.thin)
+        if self.hasBK:
             self.Gibbs_BK.gibbs(burnin=self.burnin, sample=self.sample, thin=self.thin,
                                 mean_approx=self.bk_mean_approx)
+        if self.hasSC:
+            self.suff_stats.update(self.Gibbs_SC.suff_stats)
+        if self.hasBK:
             self.suff_stats.update(self.Gibbs_BK.suff_stats)
 
     def em_iteration(self):

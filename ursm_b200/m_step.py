@@ -178,8 +178,9 @@ class LogitNormalMLE(object):
         """m_step.py:50-89."""
         import torch
         self.suff_stats = suff_stats
-        sc = suff_stats.get("_ursm_sc") if self.hasSC else None
-        bk = suff_stats.get("_ursm_bk") if self.hasBK else None
+        deref = lambda r: r() if r is not None else None  # the samplers hand out weak references
+        sc = deref(suff_stats.get("_ursm_sc")) if self.hasSC else None
+        bk = deref(suff_stats.get("_ursm_bk")) if self.hasBK else None
         if (self.hasSC and sc is None) or (self.hasBK and bk is None):
             raise _lib.UrsmError(
                 "LogitNormalMLE.update_suff_stats needs the suff_stats dict produced by "
