@@ -96,6 +96,12 @@ int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kapp
                         const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t sweep,
                         float* h_w_out, uint8_t* h_S_out, double* h_kappa_out,
                         double* h_tau_out, int32_t* h_scan_rounds);
+/* statistics that were NOT produced by this library (a suff_stats dict of the reference's own
+ * sampler, e_step_gibbs.py:228-242, handed to the M-step): installs E[S] as counts per entry
+ * (h_cnt[l][i] = exp_S * sample, an integer by construction :247) and the per-cell moments
+ * [4][L] (E kappa, E tau, E kappa^2, E tau^2), so that update_suff_stats m_step.py:50-89 and the
+ * opt_u / update_gd_coeffConst passes :108-125 can run on them */
+int ursm_sc_set_counts(ursm_sc* sc, const uint16_t* h_cnt, int32_t sample, const double* h_cellmom);
 /* parity hook for update_suffStats :245-270 as the PRODUCTION kernel folds it: burnin +
  * sample*thin gibbs_cycles (:307-312) from a caller-supplied (S, kappa, tau) with the retention
  * schedule of gibbs :299-304; returns the state after EVERY sweep -- h_w_out / h_S_out
@@ -122,7 +128,7 @@ int ursm_sc_geometry(const ursm_sc* sc, int32_t* threads, int32_t* genes_per_thr
  * ursm_bk_gibbs        gibbs(mean_approx=False) :105-117: per sweep draw_W :140-146 then
  *                       draw_Z :132-138, update_suffStats on retained sweeps
  *   d_stats (length ursm_bk_stats_len()):  exp_Zik[N*K] | sum_j exp_logW[K] |
- *                                          sum_jk exp_Zjk*exp_logW
+ *                                          sum_jk exp_Zjk*exp_logW | sampler failure count (0)
  * ursm_bk_get_sample_stats  exp_Zjk (M x K), exp_logW (K x M), exp_W (K x M)
  * freeze flags (parity hooks for the moment tests): bit0 = keep W fixed, bit1 = keep Z sums fixed
  */

@@ -143,3 +143,50 @@ def test_reference_style_driver_joint_demo(golden):
     assert np.abs(out["suff_stats"]["exp_W"] - f["mean_exp_W"]).max() < 0.01
     eS = np.asarray(out["suff_stats"]["exp_S"])
     assert eS.shape == Y.shape and np.all(eS[Y > 0] == 1)
+
+
+@pytest.mark.gpu
+def test_mstep_accepts_statistics_of_another_sampler():
+    """m_step.py:50-89 takes ANY dict with the reference's keys: here the numpy oracle's Gibbs
+    samplers (host arrays, no device handles) feed this package's M-step, which must then agree
+    with the oracle's M-step on the same dict (missing #4)."""
+    from oracle import ursm_oracle as orc
+    import ursm_b200.m_step as ms
+    N, K, L, M = 120, 3, 30, 8
+    sim = orc.simulate(N=N, K=K, L=L, M=M, seed=4)
+    Y, X, G = sim["Y"], sim["X"], sim["G"]
+    itype = [np.where(G == k)[0] for k in range(K)]
+    A = orc.init_A(Y, X, K, itype, 1e-6)
+    pk, pt, al = np.array([-1., 0.01]), np.array([N, 0.01 * N], dtype=float), np.ones(K)
+    rng = np.random.RandomState(3)
+    osc = orc.OracleGibbsSC(A, pk, pt, Y, G, itype, rng=rng)
+    osc.init_gibbs()
+    osc.gibbs(burnin=2, sample=7, thin=1)
+    obk = orc.OracleGibbsBK(A, al, X, None, rng=rng)
+    obk.init_gibbs()
+    obk.gibbs(burnin=2, sample=5, thin=1, mean_approx=False)
+    st = dict(osc.suff_stats)
+    st.update(obk.suff_stats)
+    assert not any(k.startswith("_ursm") for k in st)
+    mle = ms.LogitNormalMLE(X, Y, G, K, itype, True, True, A, al, pk, pt, 1e-6, 1, 1e-8, 6)
+    omle = orc.OracleMLE(X, Y, G, K, itype, True, True, A, al, pk, pt, 1e-6, 1, 1e-8, 6)
+    mle.update_suff_stats(dict(st))
+    omle.update_suff_stats(dict(st))
+    np.testing.assert_allclose(mle.u, omle.u, rtol=1e-10)
+    np.testing.assert_allclose(mle.gd_coeffAinv, omle.gd_coeffAinv, rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(mle.gd_coeffConst, omle.gd_coeffConst, rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(mle.compute_elbo(), omle.compute_elbo(), rtol=1e-9)
+    mle.opt_kappa_tau()
+    omle.opt_kappa_tau()
+    np.testing.assert_allclose(mle.pkappa, omle.pkappa, rtol=1e-9)
+    assert mle.opt_alpha() == omle.opt_alpha()
+    mle.opt_A_u()
+    omle.opt_A_u()
+    np.testing.assert_allclose(mle.A, omle.A, rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(mle.compute_elbo(), omle.compute_elbo(), rtol=1e-8)
+    # a dict that is not the statistic of a Gibbs run is refused, not quantised
+    bad = dict(st)
+    bad["exp_S"] = np.asarray(st["exp_S"]) * 0.999 + 1e-4 * rng.rand(L, N)
+    from ursm_b200 import _lib
+    with pytest.raises(_lib.UrsmError, match="multiple of 1/sample"):
+        mle.update_suff_stats(bad)

@@ -37,6 +37,7 @@ SIGNATURES = {
     "ursm_sc_inject": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ursm_sc_sweep_debug": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_u64, c_i32, c_vp, c_vp,
                                     c_vp, c_vp, c_vp]),
+    "ursm_sc_set_counts": (c_int, [c_vp, c_vp, c_i32, c_vp]),
     "ursm_sc_chain_debug": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_u64, c_i32, c_i32, c_i32,
                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ursm_sc_kernel_ms": (c_int, [c_vp, c_vp]),

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kWDrawThreads)
 bk_w_draw_kernel(double* W, float* W32g, const double* n_prev, double* n_next,
                  const double* alpha, long long M, int K, long long sample_offset,
                  unsigned long long key, unsigned int sweep, int prev_retained, int retained,
-                 int draw, double inv_sample, double* eZjk, double* eLogW, double* eW) {
+                 int draw, double inv_sample, double* eZjk, double* eLogW, double* eW, int* fail) {
   __shared__ double g_s[kWDrawThreads];
   const int per_block = kWDrawThreads / K;  // samples per CTA
   const int jl = threadIdx.x / K, k = threadIdx.x - jl * K;
@@ -323,7 +323,9 @@ bk_w_draw_kernel(double* W, float* W32g, const double* n_prev, double* n_next,
     if (prev_retained) eZjk[e] += n_prev[e] * inv_sample;
     if (draw) {
       Philox rng(key, 0xfffffffeu - (uint32_t)k, (uint32_t)(sample_offset + j), kPurposeBulkW | sweep);
-      gmm = gamma_mt(alpha[k] + n_prev[e], rng);
+      bool failed = false;
+      gmm = gamma_mt(alpha[k] + n_prev[e], rng, &failed);
+      if (failed) atomicAdd(fail, 1);  // never seen; the host raises if it ever is
     }
   }
   if (draw) {
@@ -441,10 +443,11 @@ __global__ void bk_mean_finalize_kernel(const double* W, double* eLogW, double* 
   eLogW[t] = log(W[t]);
 }
 
-// stats tail: sum_j E[log W_kj] (K values) and sum_jk E[Z_jk] E[log W_kj]
+// stats tail: sum_j E[log W_kj] (K values), sum_jk E[Z_jk] E[log W_kj], sampler failure count
 __global__ void bk_tail_kernel(const double* eZjk, const double* eLogW, long long M, int K,
-                               double* tail) {
+                               double* tail, const int* fail) {
   __shared__ double red[32];
+  if (threadIdx.x == 0) tail[K + 1] = fail ? (double)*fail : 0.0;
   double cross = 0.0;
   for (long long t = threadIdx.x; t < M * K; t += blockDim.x) cross += eZjk[t] * eLogW[t];
   cross = block_sum(cross, red);
@@ -576,6 +579,7 @@ static void bk_finish_create(BkShard* b) {
   b->eZjk.alloc(MK);
   b->eLogW.alloc(MK);
   b->eW.alloc(MK);
+  b->fail.alloc(1);
   b->nA.zero();
   b->nB.zero();
   URSM_CUDA(cudaDeviceSynchronize());
@@ -653,7 +657,7 @@ int ursm_bk_profile_sum(ursm_bk* bk, double* d_out, void* stream) {
 
 int64_t ursm_bk_stats_len(const ursm_bk* bk) {
   const BkShard* b = reinterpret_cast<const BkShard*>(bk);
-  return (int64_t)b->N * b->K + b->K + 1;
+  return (int64_t)b->N * b->K + b->K + 2;
 }
 
 int ursm_bk_kernel_ms(ursm_bk* bk, float* ms) {
@@ -721,7 +725,7 @@ int ursm_bk_mean_step(ursm_bk* bk, double* d_stats, void* stream) {
   bk_mean_finalize_kernel<<<mkb, 256, 0, st>>>(b->W.p, b->eLogW.p, b->eW.p, b->M, b->K);
   URSM_LAUNCH_CHECK();
   bk_tail_kernel<<<1, 1024, 0, st>>>(b->eZjk.p, b->eLogW.p, b->M, b->K,
-                                     d_stats + (size_t)b->N * b->K);
+                                     d_stats + (size_t)b->N * b->K, nullptr);
   URSM_LAUNCH_CHECK();
   bk_time_end(b, st);
   URSM_API_END
@@ -752,6 +756,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   b->eZjk.zero(st);
   b->eLogW.zero(st);
   b->eW.zero(st);
+  b->fail.zero(st);
   const size_t KN = (size_t)b->K * b->N;
   bk_cast_A_kernel<<<(unsigned)((KN + 255) / 256), 256, 0, st>>>(b->A.p, KN, b->A32.p);
   URSM_LAUNCH_CHECK();
@@ -782,7 +787,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
     bk_w_draw_kernel<<<mb, kWDrawThreads, 0, st>>>(
         b->W.p, b->W32g.p, b->nA.p, b->nB.p, b->alpha.p, b->M, b->K, b->sample_offset, key,
         (unsigned)sweep, prev_ret ? 1 : 0, retained ? 1 : 0, freezeW ? 0 : 1, inv, b->eZjk.p,
-        b->eLogW.p, b->eW.p);
+        b->eLogW.p, b->eW.p, b->fail.p);
     URSM_LAUNCH_CHECK();
     a.n_cur = b->nB.p;
     a.retained = retained ? 1 : 0;
@@ -797,7 +802,7 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
     URSM_LAUNCH_CHECK();
   }
   bk_tail_kernel<<<1, 1024, 0, st>>>(b->eZjk.p, b->eLogW.p, b->M, b->K,
-                                     d_stats + (size_t)b->N * b->K);
+                                     d_stats + (size_t)b->N * b->K, b->fail.p);
   URSM_LAUNCH_CHECK();
   bk_time_end(b, st);
   URSM_API_END

@@ -178,7 +178,8 @@ URSM_HD bool pg_attempt(const PgTilt& g, float u0, float u1, float u2, float& x)
   return u2 <= tilt * series;
 }
 
-// Convenience draw (host tests, non-critical device code): attempts until accepted.
+// Convenience draw (host tests only; the kernels run pg_attempt in their own warp loop, which has
+// no attempt limit): attempts until accepted.
 template <class RNG>
 URSM_HD float pg1_draw(float psi, RNG& rng) {
   const PgTilt g = pg_tilt(psi);
@@ -235,8 +236,10 @@ URSM_HD void normal_pair(RNG& rng, double& n0, double& n1) {
 }
 
 // Gamma(shape, 1), Marsaglia & Tsang (2000); shape < 1 via the U^(1/shape) boost.
+// `failed` (optional) is set if the rejection loop runs out of tries (probability ~ 0.05^1000:
+// a broken generator, never a legitimate draw); the value returned then is the mode, not a draw.
 template <class RNG>
-URSM_HD double gamma_mt(double shape, RNG& rng) {
+URSM_HD double gamma_mt(double shape, RNG& rng, bool* failed = nullptr) {
   double boost = 1.0;
   if (shape < 1.0) {
     boost = pow(rng.uniform_d(), 1.0 / shape);
@@ -254,6 +257,7 @@ URSM_HD double gamma_mt(double shape, RNG& rng) {
     if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
     if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
   }
+  if (failed) *failed = true;
   return boost * d;
 }
 

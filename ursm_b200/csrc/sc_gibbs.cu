@@ -1097,6 +1097,20 @@ static void sc_chain_debug(ScShard* s, const int64_t* h_S_in, const double* h_ka
     URSM_CUDA(cudaMemcpy(h_cellmom, s->cellmom.p, 4 * L * sizeof(double), cudaMemcpyDeviceToHost));
 }
 
+int ursm_sc_set_counts(ursm_sc* sc, const uint16_t* h_cnt, int32_t sample, const double* h_cellmom) {
+  URSM_API_BEGIN
+  ScShard* s = reinterpret_cast<ScShard*>(sc);
+  URSM_REQUIRE(s && h_cnt && sample >= 1 && sample <= 65535, "ursm_sc_set_counts: bad argument");
+  s->cnt_ensure(2);
+  s->sample = sample;
+  URSM_CUDA(cudaMemcpy(s->cnt.p, h_cnt, (size_t)s->L * s->N * sizeof(uint16_t),
+                       cudaMemcpyHostToDevice));
+  if (h_cellmom)
+    URSM_CUDA(cudaMemcpy(s->cellmom.p, h_cellmom, 4 * (size_t)s->L * sizeof(double),
+                         cudaMemcpyHostToDevice));
+  URSM_API_END
+}
+
 int ursm_sc_sweep_debug(ursm_sc* sc, const int64_t* h_S_in, const double* h_kappa_in,
                         const double* h_tau_in, uint64_t seed, uint64_t em_iter, int32_t sweep,
                         float* h_w_out, uint8_t* h_S_out, double* h_kappa_out, double* h_tau_out,

@@ -62,6 +62,7 @@ struct BkShard {
   DevBuf<double> lf2;            // [1024] log2 k! (modal binomial inversion)
   DevBuf<double> acc;            // [M][K] scratch (nmf numerators)
   DevBuf<double> eZjk, eLogW, eW;  // [M][K] each
+  DevBuf<int> fail;              // [1] sampler bail-outs of the last Gibbs E-step (0 in a correct run)
   bool has_params = false, has_state = false;
   int num_sms = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // bracket the last E-step's kernels

@@ -414,4 +414,7 @@ class LogitNormalGibbs_BK(object):
         st["exp_W"] = eW
         st["_ursm_bk"] = weakref.ref(self)
         st["_ursm_bk_tail"] = host[N * K:N * K + K + 1].copy()  # sum_j E log W_k | sum Zjk*logW
+        if host[N * K + K + 1] != 0:
+            raise _lib.UrsmError("bulk Gibbs kernels: %d gamma draws ran out of attempts"
+                                 % int(host[N * K + K + 1]))
         self._suff = st

@@ -181,11 +181,10 @@ class LogitNormalMLE(object):
         deref = lambda r: r() if r is not None else None  # the samplers hand out weak references
         sc = deref(suff_stats.get("_ursm_sc")) if self.hasSC else None
         bk = deref(suff_stats.get("_ursm_bk")) if self.hasBK else None
-        if (self.hasSC and sc is None) or (self.hasBK and bk is None):
-            raise _lib.UrsmError(
-                "LogitNormalMLE.update_suff_stats needs the suff_stats dict produced by "
-                "ursm_b200.e_step_gibbs samplers (device-resident E[S] counters); "
-                "there is no host fallback")
+        if self.hasSC and sc is None:
+            sc = self._adopt_foreign_sc(suff_stats)
+        if self.hasBK and bk is None:
+            bk = self._adopt_foreign_bk(suff_stats)
         self._ensure_workspace(sc, bk)
         K, N, KN = self.K, self.N, self.K * self.N
         self._push_A()
@@ -212,6 +211,77 @@ class LogitNormalMLE(object):
             self._has_cells = self.type_counts > 0
             self._pass_u(self._has_cells)
         self._refresh_host_coeffs()
+
+    # -- statistics that did not come from this package's samplers -----------------------
+    # The reference's M-step takes any dict with the keys of e_step_gibbs.py:59-66,228-242
+    # (m_step.py:50-89).  Such a dict holds host arrays; they are uploaded into a device shard
+    # built from the count matrices the constructor was given, and the device path runs as
+    # usual.  (One process only: a foreign dict carries no sharding information.)
+    def _adopt_foreign_sc(self, st):
+        import torch
+        from .e_step_gibbs import LogitNormalGibbs_SC
+        if dist.world_size() > 1:
+            raise _lib.UrsmError("suff_stats from another sampler are supported in one process only")
+        if self.SCexpr is None or self.G is None:
+            raise _lib.UrsmError("LogitNormalMLE needs SCexpr and G to adopt statistics that were "
+                                 "not produced by ursm_b200.e_step_gibbs")
+        for key in ("exp_S", "exp_kappa", "exp_tau", "exp_kappasq", "exp_tausq", "coeffA",
+                    "coeffAsq", "exp_elbo_const"):
+            if key not in st:
+                raise _lib.UrsmError("suff_stats lacks %r (e_step_gibbs.py:228-242)" % key)
+        eS = np.asarray(st["exp_S"], dtype=float)
+        # exp_S accumulates S / sample (e_step_gibbs.py:247): recover the integer counts
+        vals = np.unique(eS)
+        pos = vals[vals > 0]
+        gaps = np.diff(np.concatenate([[0.0], pos]))
+        step = gaps[gaps > 1e-9].min() if pos.size else 1.0
+        sample = int(round(1.0 / step))
+        cnt = eS * sample
+        if not (1 <= sample <= 65535) or np.abs(cnt - np.round(cnt)).max() > 1e-6 * max(sample, 1):
+            raise _lib.UrsmError("exp_S is not a multiple of 1/sample with sample <= 65535: not "
+                                 "the statistic of a Gibbs run (e_step_gibbs.py:247)")
+        sc = getattr(self, "_foreign_sc", None)
+        if sc is None:
+            itype = self.itype if self.itype is not None else \
+                [np.where(np.asarray(self.G) == k)[0] for k in range(self.K)]
+            sc = LogitNormalGibbs_SC(self.A, self.pkappa, self.ptau, self.SCexpr, self.G, itype)
+            self._foreign_sc = sc
+        L, N, K = sc.L, self.N, self.K
+        mom = np.ascontiguousarray(np.stack([np.ravel(st[k]) for k in
+                                             ("exp_kappa", "exp_tau", "exp_kappasq", "exp_tausq")]),
+                                   dtype=np.float64)
+        cnt16 = np.ascontiguousarray(np.round(cnt), dtype=np.uint16)
+        _lib.call("ursm_sc_set_counts", sc._h, _lib.ptr(cnt16), sample, _lib.ptr(mom))
+        host = np.zeros(2 * N * K + 6)
+        host[:N * K] = np.asarray(st["coeffA"], dtype=float).T.ravel()
+        host[N * K:2 * N * K] = np.asarray(st["coeffAsq"], dtype=float).T.ravel()
+        host[2 * N * K] = float(st["exp_elbo_const"])
+        host[2 * N * K + 1:2 * N * K + 5] = [mom[0].sum(), mom[2].sum(), mom[1].sum(), mom[3].sum()]
+        sc._stats.copy_(torch.from_numpy(host))
+        st["_ursm_sc_sums"] = host[2 * N * K + 1:2 * N * K + 5].copy()
+        return sc
+
+    def _adopt_foreign_bk(self, st):
+        import torch
+        if dist.world_size() > 1:
+            raise _lib.UrsmError("suff_stats from another sampler are supported in one process only")
+        for key in ("exp_Zik", "exp_Zjk", "exp_logW"):
+            if key not in st:
+                raise _lib.UrsmError("suff_stats lacks %r (e_step_gibbs.py:59-66)" % key)
+        N, K = self.N, self.K
+        eLogW = np.asarray(st["exp_logW"], dtype=float)           # K x M
+        host = np.zeros(N * K + K + 2)
+        host[:N * K] = np.asarray(st["exp_Zik"], dtype=float).T.ravel()
+        host[N * K:N * K + K] = eLogW.sum(axis=1)
+        host[N * K + K] = float((np.asarray(st["exp_Zjk"], dtype=float).T * eLogW).sum())
+
+        class _HostBulkStats(object):   # what update_suff_stats reads from a bulk sampler
+            _h = None
+        bk = _HostBulkStats()
+        bk._stats = torch.from_numpy(host).to("cuda")
+        st["_ursm_bk_tail"] = host[N * K:N * K + K + 1].copy()
+        self._foreign_bk = bk
+        return bk
 
     def _refresh_host_coeffs(self):
         """The reference's attributes `gd_coeffAinv`, `gd_coeffA`, `gd_coeffConst` (N x K) and
