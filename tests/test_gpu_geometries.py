@@ -399,9 +399,15 @@ def test_mstep_production_shapes_match_oracle(case, monkeypatch):
 # ---------------------------------------------------------------------------
 # bulk multinomial split at K = 10 (c3 / c4 shape of the type axis)
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("depth", [20.0, 3000.0])
-def test_bulk_split_moments_K10(depth):
+@pytest.mark.parametrize("split", ["lockstep", "lane"])
+@pytest.mark.parametrize("depth", [20.0, 300.0, 3000.0])
+def test_bulk_split_moments_K10(depth, split, monkeypatch):
+    """Both split kernels over the three regimes of the binomial chain -- inversion from 0
+    (depth 20), inversion from the mode (300), BTRS (3000; with `lockstep` every chain goes
+    through the hand-over list of bk_split_cold_kernel) -- against the exact moments of
+    numpy.random.multinomial (e_step_gibbs.py:137)."""
     import ursm_b200.e_step_gibbs as es
+    monkeypatch.setenv("URSM_BK_SPLIT", split)
     rs = np.random.RandomState(14)
     M, N, K = 20, 700, 10
     A = rs.dirichlet(np.ones(N) * 0.7, K).T

@@ -84,9 +84,14 @@ def test_bulk_split_moments_frozen_W(golden):
     np.testing.assert_allclose(bk.suff_stats["exp_Zik"].sum(axis=1), X.sum(axis=0), rtol=1e-12)
 
 
-def test_bulk_split_moments_large_counts():
-    """Deep samples (counts in the thousands): the BTRS branch of the binomial chain."""
+@pytest.mark.parametrize("split", ["auto", "lockstep"])
+def test_bulk_split_moments_large_counts(split, monkeypatch):
+    """Deep samples (counts in the thousands): the BTRS branch of the binomial chain, in the
+    per-lane kernel (what the library picks for such data) and through the hand-over list of
+    the lockstep kernel."""
     import ursm_b200.e_step_gibbs as es
+    if split != "auto":
+        monkeypatch.setenv("URSM_BK_SPLIT", split)
     rs = np.random.RandomState(4)
     M, N, K = 24, 96, 4
     A = rs.dirichlet(np.ones(N) * 0.7, K).T

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "samplers.cuh"
 #include "sc_shard.h"
+#include "bk_split.cuh"
 #include "../../include/ursm_b200.h"
 
 #include <algorithm>
@@ -133,186 +134,22 @@ __global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------
-// draw_Z (:132-138) for one Gibbs sweep: Z_ji. ~ Mult(X_ji, W_.j A_i. / AW_ij) as the chain
-// of K-1 conditional binomials numpy.random.multinomial uses.
-//
-// The 32 lanes of a warp are 32 bulk SAMPLES and the warp walks a range of genes: for a
-// given (gene, type) all lanes share A_ik and see similar counts and similar W, so the
-// data-dependent length of a binomial draw is nearly the same in every lane (with lanes =
-// genes, the layout of the first version, A_ik varied over orders of magnitude inside a warp
-// and 8 of 32 lanes were busy in the search loop).  Counts are read from a gene-major copy
-// of X (samples contiguous: one 128-byte line per warp and gene).  sum_i Z_jik is private to
-// a lane (a shared-memory column per thread, flushed once per CTA); sum_j Z_jik is a warp
-// reduction + one shared-memory atomic per (gene, type), flushed once per CTA.  Z (M x N x K)
-// and AW (N x M) never exist.
-// Each binomial is an inversion from the MODE (samplers.cuh::binom_mode_try: ~1 + 1.6 sigma
-// atoms instead of 1 + n r from zero; log2 k! table in shared memory) for n < 1024 and
-// n r <= 32; deeper items take the resumable fp32 state machine (inversion from 0 for
-// n r <= 20, BTRS above) out of line.  Conditional probabilities are ratios of positive
-// masses (the mass of the types still to come is tracked in fp64).  The RNG is keyed on the
-// gene id and the GLOBAL sample id, so results do not depend on the sharding.
-//
-// A CTA = 8 warps = `gpc` sample groups x 8/gpc interleaved gene phases, for one range of
-// genes; grid = gene ranges x rows of gpc sample groups.
-// ---------------------------------------------------------------------------
-constexpr int kSplitThreads = 256;
-
-struct BkSplitArgs {
-  const float* Xt;      // [N][Mpad] counts, gene-major
-  const float* A32;     // [K][N] fp32 A^T
-  const float* W32g;    // [ngroups][K][32] fp32 W of this sweep
-  const double* lf2;    // [URSM_BINOM_TABLE] log2 k!
-  double* n_cur;        // [M][K] accumulates this sweep's sum_i Z (zero on entry)
-  double* sumI;         // [K][N] exp_Zik accumulator
-  long long M, sample_offset;
-  int Mpad, N, K, ngroups, gpc, genes_per_cta;
-  double inv_sample;
-  int retained;
-  unsigned long long key;
-  PhiloxKeys rk;
-  unsigned int sweep;
-};
-
-// deep items (n >= 1024 or n r > 32): the resumable fp32 state machine, out of line
-__device__ __noinline__ int binom_deep(int n, float p, float pc, float u, unsigned long long key,
-                                       uint32_t gene, uint32_t jg, uint32_t ctr2, int k,
-                                       const double* lf2) {
-  BinomState b;
-  binom_begin(b, n, p, pc, u);
-  int extra = 0;  // further Philox blocks of this item: BTRS attempts, inversion restarts
-  while (b.mode != kBinDone) {
-    if (b.mode == kBinInv) {
-      binom_inv_chunk4(b);
-    } else {
-      uint32_t e0, e1, e2, e3;
-      philox_block(key, gene, jg, ctr2, 0x100u + (uint32_t)(k << 8) + (uint32_t)extra, e0, e1, e2, e3);
-      ++extra;
-      if (b.mode == kBinBtrs) {
-        binom_btrs_attempt(b, u01(e0), u01(e1), lf2);
-        if (b.mode != kBinDone) binom_btrs_attempt(b, u01(e2), u01(e3), lf2);
-      } else {  // kBinRetry
-        binom_inv_start(b, u01(e0));
-      }
-    }
-  }
-  return b.result;
-}
-
-#ifndef URSM_BK_MINBLOCKS
-#define URSM_BK_MINBLOCKS 4
-#endif
-__global__ void __launch_bounds__(kSplitThreads, URSM_BK_MINBLOCKS) bk_split_kernel(BkSplitArgs a) {
-  extern __shared__ __align__(16) unsigned char split_smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = a.K, N = a.N, gpc = a.gpc;
-  const int nphase = (kSplitThreads / 32) / gpc;
-  const int grp_local = warp % gpc, phase = warp / gpc;
-  const int grp = blockIdx.y * gpc + grp_local;
-  const bool live = grp < a.ngroups && phase < nphase;
-  const int g0 = blockIdx.x * a.genes_per_cta;
-  const int ng = min(a.genes_per_cta, N - g0);
-  double* lf2 = reinterpret_cast<double*>(split_smem);                       // [URSM_BINOM_TABLE]
-  float* Wsm = reinterpret_cast<float*>(lf2 + URSM_BINOM_TABLE);              // [gpc][K][32]
-  unsigned int* accJ = reinterpret_cast<unsigned int*>(Wsm + gpc * K * 32) + tid;  // [K][T] own column
-  unsigned int* accI = accJ - tid + K * kSplitThreads;                         // [genes_per_cta][K]
-  for (int t = tid; t < URSM_BINOM_TABLE; t += kSplitThreads) lf2[t] = a.lf2[t];
-  for (int t = tid; t < gpc * K * 32; t += kSplitThreads) {
-    const int gl = t / (K * 32);
-    const int gg = blockIdx.y * gpc + gl;
-    Wsm[t] = gg < a.ngroups ? a.W32g[(size_t)gg * K * 32 + (t - gl * K * 32)] : 0.f;
-  }
-  for (int k = 0; k < K; ++k) accJ[k * kSplitThreads] = 0u;
-  const bool keepI = a.retained != 0;
-  if (keepI)
-    for (int t = tid; t < ng * K; t += kSplitThreads) accI[t] = 0u;
-  __syncthreads();
-  const uint32_t ctr2 = kPurposeBulkZ | a.sweep;
-  const float* Wj = Wsm + grp_local * K * 32 + lane;  // W_jk at Wj[k * 32]
-  const uint32_t jg = (uint32_t)(a.sample_offset + (long long)grp * 32 + lane);
-
-  if (live) {
-    for (int gl = phase; gl < ng; gl += nphase) {
-      const int gene = g0 + gl;
-      const float xf = a.Xt[(size_t)gene * a.Mpad + (size_t)grp * 32 + lane];
-      int rem = (int)xf;
-      if (__all_sync(0xffffffffu, rem == 0)) continue;  // nothing to split for these samples
-      const float* Ai = a.A32 + gene;                    // A_ik at Ai[k * N] (warp-uniform)
-      // AW_ij and the mass of the types still to come (fp64: exact enough down to the last type)
-      double rest = 0.0;
-      for (int k = 0; k < K; ++k) rest += (double)(Wj[k * 32] * __ldg(Ai + (size_t)k * N));
-      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-#pragma unroll 1
-      for (int k = 0; k < K; ++k) {
-        int z;
-        if (k == K - 1) {
-          z = rem;  // the last type takes what is left
-        } else {
-          if ((k & 3) == 0)
-            philox_block(a.rk, (uint32_t)gene, jg, ctr2, (uint32_t)(k >> 2), w0, w1, w2, w3);
-          const uint32_t wk = (k & 3) == 0 ? w0 : ((k & 3) == 1 ? w1 : ((k & 3) == 2 ? w2 : w3));
-          const float qk = Wj[k * 32] * __ldg(Ai + (size_t)k * N);
-          const double after = fmax(rest - (double)qk, 0.0);
-          const float inv = URSM_RCP((float)rest);
-          // P(type k | not yet assigned) and its complement, each formed from its own mass
-          const float p = qk * inv, pc = (float)after * inv;
-          rest = after;
-          const bool flip = p > 0.5f;
-          const float r = flip ? pc : p, rc = flip ? p : pc;
-          if (rem <= 0 || !(r > 0.0f)) {
-            z = flip ? rem : 0;
-          } else if (binom_use_mode(rem, (float)rem * r)) {
-            int x = binom_mode_try(rem, r, rc, u01(wk), lf2);
-            for (int extra = 0; x < 0; ++extra) {  // uniform beyond the fp32 mass sum (~1e-6): redraw
-              uint32_t e0, e1, e2, e3;
-              philox_block(a.rk, (uint32_t)gene, jg, ctr2, 0x100u + (uint32_t)(k << 8) + (uint32_t)extra,
-                           e0, e1, e2, e3);
-              x = binom_mode_try(rem, r, rc, u01(e0), lf2);
-            }
-            z = flip ? rem - x : x;
-          } else {
-            z = binom_deep(rem, p, pc, u01(wk), a.key, (uint32_t)gene, jg, ctr2, k, lf2);
-          }
-          rem -= z;
-        }
-        accJ[k * kSplitThreads] += (unsigned int)z;
-        if (keepI) {
-          const unsigned int tot = __reduce_add_sync(0xffffffffu, (unsigned int)z);
-          if (lane == 0 && tot != 0u) atomicAdd(&accI[gl * K + k], tot);
-        }
-      }
-    }
-    const long long j = (long long)grp * 32 + lane;
-    if (j < a.M)
-      for (int k = 0; k < K; ++k) {
-        const unsigned int v = accJ[k * kSplitThreads];
-        if (v != 0u) atomicAdd(&a.n_cur[j * K + k], (double)v);
-      }
-  }
-  if (keepI) {
-    __syncthreads();
-    for (int t = tid; t < ng * K; t += kSplitThreads) {
-      const unsigned int v = accI[t];
-      const int gl = t / K, k = t - gl * K;
-      if (v != 0u) atomicAdd(&a.sumI[(size_t)k * N + g0 + gl], (double)v * a.inv_sample);
-    }
-  }
-}
-
 // One Gibbs sweep's W step (:140-146) plus the per-sample part of update_suffStats (:69-78).
 // One thread per (sample, type): W_j ~ Dir(alpha + sum_i Z_j.) is K independent gammas
 // (Marsaglia-Tsang, fp64, each from its own Philox stream keyed on the global sample id and
 // the type) that the sample's K threads then normalise through shared memory in a fixed
 // order.  Also writes the fp32 copy of W in the split kernel's layout ([group][type][lane])
-// and zeroes the buffer the split kernel accumulates into.
+// and zeroes the buffer the split kernel accumulates into (and its hand-over counter).
 constexpr int kWDrawThreads = 128;
 
 __global__ void __launch_bounds__(kWDrawThreads)
 bk_w_draw_kernel(double* W, float* W32g, const double* n_prev, double* n_next,
                  const double* alpha, long long M, int K, long long sample_offset,
                  unsigned long long key, unsigned int sweep, int prev_retained, int retained,
-                 int draw, double inv_sample, double* eZjk, double* eLogW, double* eW, int* fail) {
+                 int draw, double inv_sample, double* eZjk, double* eLogW, double* eW, int* fail,
+                 unsigned int* cold_count) {
   __shared__ double g_s[kWDrawThreads];
+  if (cold_count && blockIdx.x == 0 && threadIdx.x == 0) *cold_count = 0u;  // this sweep's hand-over list
   const int per_block = kWDrawThreads / K;  // samples per CTA
   const int jl = threadIdx.x / K, k = threadIdx.x - jl * K;
   const long long j = (long long)blockIdx.x * per_block + jl;
@@ -354,14 +191,30 @@ __global__ void bk_gibbs_final_kernel(const double* n_last, double* eZjk, size_t
   if (t < n) eZjk[t] += n_last[t] * inv;
 }
 
-// A^T (fp64, [K][N]) -> fp32
-__global__ void bk_cast_A_kernel(const double* A, size_t n, float* out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)A[i];
+// A^T (fp64, [K][N]) -> fp32 by position (`order[pos]` = gene id, null: natural order), and the
+// type with the largest A_ik of every position (the split chain draws it last)
+__global__ void bk_cast_A_kernel(const double* A, int N, int K, const int* order, float* out,
+                                 unsigned char* kmax) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= N) return;
+  const int gene = order ? order[pos] : pos;
+  int best = 0;
+  double vbest = -1.0;
+  for (int k = 0; k < K; ++k) {
+    const double v = A[(size_t)k * N + gene];
+    out[(size_t)k * N + pos] = (float)v;
+    if (v > vbest) {
+      vbest = v;
+      best = k;
+    }
+  }
+  if (kmax) kmax[pos] = (unsigned char)best;
 }
 
-// X [M][N] -> Xt [N][Mpad] (gene-major, zero padding), 32 x 32 tiles through shared memory
-__global__ void bk_transpose_kernel(const float* X, long long M, int N, int Mpad, float* Xt) {
+// X [M][N] -> Xt [N][Mpad] (gene-major, zero padding; row of gene i = rank[i], null: i),
+// 32 x 32 tiles through shared memory
+__global__ void bk_transpose_kernel(const float* X, long long M, int N, int Mpad, const int* rank,
+                                    float* Xt) {
   __shared__ float tile[32][33];
   const long long j0 = (long long)blockIdx.y * 32;
   const int i0 = blockIdx.x * 32;
@@ -374,51 +227,17 @@ __global__ void bk_transpose_kernel(const float* X, long long M, int N, int Mpad
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int i = i0 + r;
     const long long j = j0 + threadIdx.x;
-    if (i < N && j < Mpad) Xt[(size_t)i * Mpad + j] = tile[threadIdx.x][r];
+    if (i < N && j < Mpad) Xt[(size_t)(rank ? rank[i] : i) * Mpad + j] = tile[threadIdx.x][r];
   }
 }
 
-// Launch geometry of the split kernel.  gpc sample groups share a CTA (their per-gene sums
-// meet in shared memory before one global atomic per gene and type); the gene ranges are
-// sized so that the grid is a whole number of waves of 4 CTAs per SM.
-struct BkSplitGeom {
-  int ngroups, gpc, rows, genes_per_cta, gx;
-  size_t smem;
-};
-
-static BkSplitGeom bk_split_geometry(const BkShard* b) {
-  BkSplitGeom g;
-  const int K = b->K;
-  g.ngroups = (int)((b->M + 31) / 32);
-  g.gpc = 1;
-  for (int p = 8; p >= 2; p >>= 1)
-    if (g.ngroups % p == 0 || (p == 8 && g.ngroups >= 40)) {
-      g.gpc = p;
-      break;
-    }
-  if (const char* e = getenv("URSM_BK_GROUPS_PER_CTA")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4 || v == 8) g.gpc = v;
-  }
-  g.rows = (g.ngroups + g.gpc - 1) / g.gpc;
-  int per_sm = 4;
-  if (const char* e = getenv("URSM_BK_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
-  const long long wave = (long long)per_sm * b->num_sms;
-  const int max_genes = std::max(8, (16 * 1024) / (4 * K));  // accI tile <= 16 KB
-  long long gx = std::max<long long>(1, wave / g.rows);
-  gx = std::max<long long>(gx, (b->N + max_genes - 1) / max_genes);
-  gx = std::min<long long>(gx, b->N);
-  // whole waves: round the CTA count up to a multiple of `wave` when several waves are needed
-  if (gx * g.rows > wave) {
-    const long long waves = (gx * g.rows + wave - 1) / wave;
-    gx = std::min<long long>(b->N, std::max<long long>(gx, waves * wave / g.rows));
-  }
-  g.genes_per_cta = (int)((b->N + gx - 1) / gx);
-  g.gx = (b->N + g.genes_per_cta - 1) / g.genes_per_cta;
-  g.smem = (size_t)URSM_BINOM_TABLE * 8 + (size_t)g.gpc * K * 32 * 4 + (size_t)K * kSplitThreads * 4 +
-           (size_t)g.genes_per_cta * K * 4;
-  URSM_REQUIRE(g.rows <= 65535, "bulk split kernel: too many sample groups");
-  return g;
+// how many counts are 1024 or more (the lockstep split kernel hands those chains over)
+__global__ void bk_count_deep_kernel(const float* X, size_t n, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+    c += X[t] >= (float)URSM_BINOM_TABLE;
+  c = __reduce_add_sync(0xffffffffu, (unsigned int)c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // W_kj <- W_kj * numer_jk + alpha_k - 1, renormalised over k (:159-164)
@@ -524,10 +343,12 @@ __global__ void bk_colsum_kernel(const float* X, long long M, int N, double* out
   out[i] = s;
 }
 
-// Inputs of the Gibbs split kernel that never change during a fit: the gene-major copy of X,
-// the log2 k! table, and the guard for the kernel's 32-bit accumulators.
+// Inputs of the Gibbs split kernels that never change during a fit: the choice of kernel, the
+// gene-major copy of X (by position for the lockstep kernel), the log2 k! table, the hand-over
+// list, and the guard for the kernels' 32-bit accumulators.
 static void bk_build_gibbs_inputs(BkShard* b) {
   const int N = b->N;
+  std::vector<double> colsum(N);
   {
     // sum_j Z_jik <= the gene's total count and sum_i Z_jik <= the sample's total count
     DevBuf<double> cs, rs;
@@ -536,11 +357,11 @@ static void bk_build_gibbs_inputs(BkShard* b) {
     bk_colsum_kernel<<<(N + 255) / 256, 256>>>(b->X, b->M, N, cs.p);
     URSM_LAUNCH_CHECK();
     launch_rowsum(b->X, b->M, N, rs.p, 0);
-    std::vector<double> h(N), hr((size_t)b->M);
-    URSM_CUDA(cudaMemcpy(h.data(), cs.p, N * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<double> hr((size_t)b->M);
+    URSM_CUDA(cudaMemcpy(colsum.data(), cs.p, N * sizeof(double), cudaMemcpyDeviceToHost));
     URSM_CUDA(cudaMemcpy(hr.data(), rs.p, hr.size() * sizeof(double), cudaMemcpyDeviceToHost));
     double worst = 0.0;
-    for (double v : h) worst = std::max(worst, v);
+    for (double v : colsum) worst = std::max(worst, v);
     for (double v : hr) worst = std::max(worst, v);
     URSM_REQUIRE(worst < 4294967296.0, "bulk Gibbs kernel: a gene's or a sample's total count "
                                        "reaches 2^32 (32-bit accumulators)");
@@ -551,16 +372,53 @@ static void bk_build_gibbs_inputs(BkShard* b) {
     b->lf2.alloc(URSM_BINOM_TABLE);
     URSM_CUDA(cudaMemcpy(b->lf2.p, lf2.data(), lf2.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
+  // which split kernel: lockstep (+ hand-over list for the chains that reach BTRS territory) unless
+  // a sizeable part of the counts is that deep, where the per-lane kernel does all of them
+  unsigned long long n_deep = 0;
+  {
+    DevBuf<unsigned long long> d;
+    d.alloc(1);
+    d.zero();
+    bk_count_deep_kernel<<<4 * b->num_sms, 256>>>(b->X, (size_t)b->M * N, d.p);
+    URSM_LAUNCH_CHECK();
+    URSM_CUDA(cudaMemcpy(&n_deep, d.p, sizeof n_deep, cudaMemcpyDeviceToHost));
+  }
+  const double cells = (double)b->M * N;
+  b->lane_kernel = (double)n_deep > 0.05 * cells;
+  if (const char* e = getenv("URSM_BK_SPLIT")) {  // "lane" / "lockstep": A/B runs and tests
+    if (!strcmp(e, "lane")) b->lane_kernel = true;
+    if (!strcmp(e, "lockstep")) b->lane_kernel = false;
+  }
   const int ngroups = (int)((b->M + 31) / 32);
   b->Mpad = ngroups * 32;
   b->A32.alloc((size_t)b->K * N);
   b->W32g.alloc((size_t)ngroups * b->K * 32);
   b->W32g.zero();
   b->Xt.alloc((size_t)N * b->Mpad);
+  DevBuf<int> rank;
+  if (!b->lane_kernel) {
+    // positions: genes by decreasing total count, dealt round-robin to the CTAs
+    std::vector<int> order(N), rk(N);
+    for (int i = 0; i < N; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return colsum[x] > colsum[y]; });
+    for (int pos = 0; pos < N; ++pos) rk[order[pos]] = pos;
+    b->order.alloc(N);
+    rank.alloc(N);
+    b->kmax.alloc(N);
+    URSM_CUDA(cudaMemcpy(b->order.p, order.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    URSM_CUDA(cudaMemcpy(rank.p, rk.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    // every chain handed over starts at a count of 1024 or more; redraws are ~1e-7 of the draws
+    const double cap = (double)n_deep + 4096.0 + 1e-5 * cells * b->K;
+    URSM_REQUIRE(cap < 4.0e9, "bulk Gibbs kernel: hand-over list too large");
+    b->cold_cap = (unsigned int)cap;
+    b->cold_list.alloc(b->cold_cap);
+    b->cold_count.alloc(1);
+    b->cold_count.zero();
+  }
   for (long long j0 = 0; j0 < b->Mpad; j0 += 32LL * 32768) {
     const long long rows = std::min<long long>(32LL * 32768, b->Mpad - j0);
     bk_transpose_kernel<<<dim3((N + 31) / 32, (unsigned)(rows / 32)), dim3(32, 8)>>>(
-        b->X + (size_t)j0 * N, b->M - j0, N, b->Mpad, b->Xt.p + j0);
+        b->X + (size_t)j0 * N, b->M - j0, N, b->Mpad, rank.p, b->Xt.p + j0);
     URSM_LAUNCH_CHECK();
   }
   URSM_CUDA(cudaDeviceSynchronize());
@@ -743,12 +601,19 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   const unsigned long long key = seed + 0x9E3779B97F4A7C15ull * (em_iter + 1) + 0x5bd1e995ull;
   const double inv = 1.0 / sample;
   const size_t MK = (size_t)b->M * b->K;
-  const BkSplitGeom g = bk_split_geometry(b);
-  static size_t configured = 0;
-  if (g.smem > 48 * 1024 && g.smem > configured) {
-    URSM_CUDA(cudaFuncSetAttribute(bk_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)g.smem));
-    configured = g.smem;
+  const BkSplitGeom g = bk_split_geometry(b->M, b->N, b->K, b->num_sms);
+  URSM_REQUIRE(g.rows <= 65535, "bulk split kernel: too many sample groups");
+  const size_t smem = b->lane_kernel ? g.smem_lane : g.smem;
+  URSM_REQUIRE(smem <= device_smem_optin(), "bulk split kernel: too many cell types for shared memory");
+  static size_t configured[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > configured[b->lane_kernel]) {
+    if (b->lane_kernel)
+      URSM_CUDA(cudaFuncSetAttribute(bk_split_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    else
+      URSM_CUDA(cudaFuncSetAttribute(bk_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    configured[b->lane_kernel] = smem;
   }
   const unsigned mb = (unsigned)((b->M + (kWDrawThreads / b->K) - 1) / (kWDrawThreads / b->K));
   bk_time_begin(b, st);
@@ -757,8 +622,8 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   b->eLogW.zero(st);
   b->eW.zero(st);
   b->fail.zero(st);
-  const size_t KN = (size_t)b->K * b->N;
-  bk_cast_A_kernel<<<(unsigned)((KN + 255) / 256), 256, 0, st>>>(b->A.p, KN, b->A32.p);
+  bk_cast_A_kernel<<<(unsigned)((b->N + 255) / 256), 256, 0, st>>>(b->A.p, b->N, b->K, b->order.p, b->A32.p,
+                                                               b->kmax.p);
   URSM_LAUNCH_CHECK();
   BkSplitArgs a;
   memset(&a, 0, sizeof a);
@@ -766,6 +631,12 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
   a.A32 = b->A32.p;
   a.W32g = b->W32g.p;
   a.lf2 = b->lf2.p;
+  a.order = b->order.p;
+  a.kmax = b->kmax.p;
+  a.cold_list = b->cold_list.p;
+  a.cold_count = b->cold_count.p;
+  a.cold_cap = b->cold_cap;
+  a.fail = b->fail.p;
   a.sumI = d_stats;
   a.M = b->M;
   a.sample_offset = b->sample_offset;
@@ -787,13 +658,21 @@ int ursm_bk_gibbs(ursm_bk* bk, int32_t burnin, int32_t sample, int32_t thin, uin
     bk_w_draw_kernel<<<mb, kWDrawThreads, 0, st>>>(
         b->W.p, b->W32g.p, b->nA.p, b->nB.p, b->alpha.p, b->M, b->K, b->sample_offset, key,
         (unsigned)sweep, prev_ret ? 1 : 0, retained ? 1 : 0, freezeW ? 0 : 1, inv, b->eZjk.p,
-        b->eLogW.p, b->eW.p, b->fail.p);
+        b->eLogW.p, b->eW.p, b->fail.p, b->cold_count.p);
     URSM_LAUNCH_CHECK();
     a.n_cur = b->nB.p;
     a.retained = retained ? 1 : 0;
     a.sweep = (unsigned)sweep;
-    bk_split_kernel<<<dim3(g.gx, g.rows), kSplitThreads, g.smem, st>>>(a);
-    URSM_LAUNCH_CHECK();
+    if (b->lane_kernel) {
+      bk_split_lane_kernel<<<dim3(g.gx, g.rows), kSplitThreads, smem, st>>>(a);
+      URSM_LAUNCH_CHECK();
+    } else {
+      bk_split_kernel<false><<<dim3(g.gx, g.rows), kSplitThreads, smem, st>>>(a);
+      URSM_LAUNCH_CHECK();
+      // grid for the expected list (its capacity when counts reach 1024), early exit beyond it
+      bk_split_cold_kernel<<<(b->cold_cap + 127) / 128, 128, 0, st>>>(a);
+      URSM_LAUNCH_CHECK();
+    }
     if (!freezeZ) std::swap(b->nA.p, b->nB.p);  // (frozen: the sums W is drawn from stay fixed)
     prev_ret = retained;
   }

@@ -62,6 +62,13 @@ struct BkShard {
   DevBuf<double> lf2;            // [1024] log2 k! (modal binomial inversion)
   DevBuf<double> acc;            // [M][K] scratch (nmf numerators)
   DevBuf<double> eZjk, eLogW, eW;  // [M][K] each
+  DevBuf<int> order;             // [N] lockstep split kernel: gene id of every position (genes by
+                                 // decreasing total count); Xt / A32 / kmax are stored by position
+  DevBuf<unsigned char> kmax;    // [N] type with the largest A_ik (drawn last), by position
+  DevBuf<uint4> cold_list;       // chains the lockstep kernel hands to bk_split_cold_kernel
+  DevBuf<unsigned int> cold_count;
+  unsigned int cold_cap = 0;
+  bool lane_kernel = false;      // deep counts: the per-lane split kernel does every chain
   DevBuf<int> fail;              // [1] sampler bail-outs of the last Gibbs E-step (0 in a correct run)
   bool has_params = false, has_state = false;
   int num_sms = 0;
