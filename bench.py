@@ -627,11 +627,11 @@ def gpu_run(args, cfg):
                               "source": "instructions per update from the ncu capture under "
                                         "profiles/ (smsp__inst_executed.sum / updates)"}}
     elif bk_ms:
-        passes = sweeps if args.bulk_mode == "gibbs" else 2  # mean update: two passes over X
+        passes = sweeps if args.bulk_mode == "gibbs" else 3  # mean update: three passes over X
         alg_bytes = 4.0 * Ml * N * passes
         achieved = alg_bytes / (bk_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "bk_split_kernel (all sweeps)" if args.bulk_mode == "gibbs"
-                    else "bk_tile_kernel<KMAX,0/1> (mean update, 2 passes)",
+                    else "bk_mean_rows_kernel x2 + bk_mean_cols_kernel (mean update, 3 passes)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "kernel_ms": bk_ms,
                     "bytes_per_update": 4.0}

@@ -1,16 +1,20 @@
 // Bulk-sample E-step for sm_100a: e_step_gibbs.py:19-164.
 //
-// Data flow: the reference materialises Z (M x N x K fp64) and
-// AW (N x M) every sweep; here neither exists.  One "tile" kernel owns a tile of
-// genes (A rows live in registers for the whole kernel) and walks a chunk of bulk
-// samples; AW_ij is a K-term dot product in registers, the K-way split of X_ji is
-// consumed on the spot into
-//    sum_i Z_jik  (warp reduction -> one atomic per warp, sample, type)   and
-//    sum_j Z_jik  (register accumulators, flushed once per CTA),
-// so HBM sees X exactly once per pass (4 B per (sample, gene)).
-//   mode 0: numerators of get_nmf_W (:157-164)
-//   mode 1: draw_Z_mean (:149-155) + update_suffStats(1) (:69-78)
-// (draw_Z (:132-138), the Gibbs mode, is bk_split_kernel below)
+// Data flow: the reference materialises Z (M x N x K fp64) and AW (N x M)
+// every sweep; here neither exists.
+//
+// The deterministic mode (`mean_approx`, the command line's default) is three streaming passes
+// over the counts, each free of cross-lane reductions because the thread owns the index its
+// sums run over:
+//   bk_mean_rows_kernel   lanes = samples (gene-major copy of X): sum_i A_ik X_ji / AW_ij
+//                         -- the numerators of get_nmf_W (:157-164) and, after the W update,
+//                         E[Z_jk] = W_jk x that sum (draw_Z_mean :149-155, update_suffStats :69-78)
+//   bk_mean_cols_kernel   lanes = genes (X as given): E[Z_ik] = A_ik sum_j W_jk X_ji / AW_ij
+// AW_ij is a K-term dot product in registers against a broadcast shared-memory row; X_ji / AW_ij
+// is one MUFU reciprocal refined by two Newton steps in fp64 (1 ulp).  fp64 throughout (the
+// reference is fp64 and the statistics are pinned to 1e-8): the passes are bound by the fp64
+// pipe (2 K + 6 DFMA-class instructions per count), not by HBM.
+// (draw_Z (:132-138), the Gibbs mode, is bk_split.cuh)
 #include "common.cuh"
 #include "samplers.cuh"
 #include "sc_shard.h"
@@ -21,117 +25,145 @@
 
 namespace ursm {
 
-constexpr int kBkThreads = 256;
+constexpr int kMeanThreads = 128;
+constexpr int kMeanBatch = 8;  // counts in flight per thread
 
-struct BkTileArgs {
-  const float* X;      // [M][N]
-  const double* A;     // [K][N]
-  const double* W;     // [M][K]
-  long long M;
-  int N, K;
-  long long sample_offset;
-  int chunk;           // samples per grid.y slice
-  double* sumJ;        // [M][K]  mode 0: nmf numerators; 1: exp_Zjk
-  double* sumI;        // [K][N]  mode 1: exp_Zik accumulator
-  double scaleI;       // 1/sample
-};
-
-// Sums P (a power of two <= 32) values per lane over the 32 lanes of a warp.  Exchange
-// `off` = 16, 8, ...: the lane with that bit set keeps the upper half of its live values
-// and receives the partner's upper half, the other lane the lower halves.  Returns the
-// index of the value whose total ends up in v[0] of this lane (-1 for lanes that hold a
-// duplicate).
-template <int P>
-__device__ __forceinline__ int warp_transpose_reduce(double (&v)[P], int lane) {
-  int idx = 0;
-  int off = 16;
-#pragma unroll
-  for (int c = P / 2; c >= 1; c /= 2) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < c; ++i) {
-      const double send = up ? v[i] : v[i + c];
-      const double recv = __shfl_xor_sync(0xffffffffu, send, off);
-      v[i] = (up ? v[i + c] : v[i]) + recv;
-    }
-    if (up) idx += c;
-    off >>= 1;
-  }
-  bool owner = true;
-  for (; off >= 1; off >>= 1) {  // P < 32: the remaining lanes hold partial sums of the same index
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-    if (lane & off) owner = false;
-  }
-  return owner ? idx : -1;
+// 1 / a for a normal positive double: MUFU reciprocal of the float, two Newton steps (1 ulp)
+__device__ __forceinline__ double rcp_newton(double a) {
+  double r = (double)URSM_RCP((float)a);
+  r = fma(r, fma(-a, r, 1.0), r);
+  r = fma(r, fma(-a, r, 1.0), r);
+  return r;
 }
 
-template <int KMAX, int MODE>
-__global__ void __launch_bounds__(kBkThreads) bk_tile_kernel(BkTileArgs a) {
-  constexpr int P = KMAX <= 4 ? 4 : (KMAX <= 8 ? 8 : (KMAX <= 16 ? 16 : 32));
-  extern __shared__ double bk_smem[];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int K = a.K, N = a.N;
-  const long long j0 = (long long)blockIdx.y * a.chunk;
-  const long long j1 = min(a.M, j0 + a.chunk);
-  const int nloc = (int)(j1 - j0);
-  double* Wsm = bk_smem;             // [nloc][K] W rows of this CTA's samples
-  double* Jsm = bk_smem + nloc * K;  // [nloc][K] CTA-level sums over genes
-  // the thread's A row and its sum_j accumulators live in private shared-memory columns
-  // (registers are needed for the K-wide butterfly below)
-  double* Ar = bk_smem + 2 * a.chunk * K + tid;   // [K][T]
-  double* accI = Ar + K * kBkThreads;              // [K][T]
-  for (int t = tid; t < nloc * K; t += kBkThreads) {
-    Wsm[t] = a.W[j0 * K + t];
-    Jsm[t] = 0.0;
-  }
-  const int gi = blockIdx.x * kBkThreads + tid;
-  const bool in = gi < N;
-  for (int k = 0; k < K; ++k) {
-    Ar[k * kBkThreads] = in ? a.A[(size_t)k * N + gi] : 0.0;
-    accI[k * kBkThreads] = 0.0;
-  }
+// Both kernels are instantiated for KP = K rounded up to one of a few sizes; the shared-memory
+// rows and the register copies are zero-padded to KP, so the K-loops carry no bounds tests.
+//
+// out[j][k] += (premul ? W_jk : 1) x sum_{i in the CTA's gene chunk} A_ik X_ji / AW_ij
+// grid = (gene chunks, groups of kMeanThreads samples); thread = one sample
+template <int KP>
+__global__ void __launch_bounds__(kMeanThreads)
+bk_mean_rows_kernel(const float* Xt, const double* A, const double* W, long long M, int Mpad, int N,
+                    int K, int gchunk, int premul, double* out) {
+  extern __shared__ double mean_smem[];  // [gchunk][KP] A rows of the chunk
+  const int tid = threadIdx.x;
+  const int g0 = blockIdx.x * gchunk, ng = min(gchunk, N - g0);
+  for (int k = 0; k < KP; ++k)
+    for (int gl = tid; gl < ng; gl += kMeanThreads)
+      mean_smem[gl * KP + k] = k < K ? A[(size_t)k * N + g0 + gl] : 0.0;
   __syncthreads();
-
-  for (int jl = 0; jl < nloc; ++jl) {
-    const long long j = j0 + jl;
-    const double* Wj = Wsm + jl * K;
-    const float xf = in ? a.X[(size_t)j * N + gi] : 0.f;
-    const bool active = xf != 0.f;  // zero counts contribute nothing in any mode
-    double aw = 0.0;
+  const long long j = (long long)blockIdx.y * kMeanThreads + tid;
+  if (j >= Mpad) return;
+  const bool on = j < M;
+  double w[KP], acc[KP];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) aw += Wj[k] * Ar[k * kBkThreads];
-    const double r = active ? (double)xf / aw : 0.0;
-    double v[P];
+  for (int k = 0; k < KP; ++k) {
+    w[k] = (on && k < K) ? W[j * K + k] : 0.0;
+    acc[k] = 0.0;
+  }
+  if (!on) w[0] = 1.0;  // (padding lanes: x = 0, any positive AW)
+  const float* xp = Xt + (size_t)g0 * Mpad + j;
+  // counts are fetched kMeanBatch genes at a time, one batch ahead of the arithmetic
+  float xn[kMeanBatch];
 #pragma unroll
-    for (int k = 0; k < P; ++k) {
-      v[k] = 0.0;
-      if (k < KMAX && k < K) {
-        if (MODE == 0) {
-          v[k] = Ar[k * kBkThreads] * r;
-        } else {
-          v[k] = Wj[k] * Ar[k * kBkThreads] * r;
-          accI[k * kBkThreads] += v[k];
-        }
+  for (int q = 0; q < kMeanBatch; ++q) xn[q] = (q < ng) ? __ldg(xp + (size_t)q * Mpad) : 0.f;
+  for (int gb = 0; gb < ng; gb += kMeanBatch) {
+    float xb[kMeanBatch];
+#pragma unroll
+    for (int q = 0; q < kMeanBatch; ++q) {  // this batch; the next one is requested before the arithmetic
+      xb[q] = xn[q];
+      const int gq = gb + kMeanBatch + q;
+      xn[q] = (gq < ng) ? __ldg(xp + (size_t)gq * Mpad) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < kMeanBatch; ++q) {
+      if (gb + q >= ng) break;
+      const double* Ag = mean_smem + (gb + q) * KP;
+      double a[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) a[k] = Ag[k];
+      double aw0 = 0.0, aw1 = 0.0;
+#pragma unroll
+      for (int k = 0; k + 1 < KP; k += 2) {
+        aw0 = fma(w[k], a[k], aw0);
+        aw1 = fma(w[k + 1], a[k + 1], aw1);
       }
+      if (KP & 1) aw0 = fma(w[KP - 1], a[KP - 1], aw0);
+      const double r = (double)xb[q] * rcp_newton(aw0 + aw1);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) acc[k] = fma(a[k], r, acc[k]);
     }
-    // sum over the 32 genes of the warp, all K types at once: a butterfly that halves
-    // the number of live values per lane at every exchange (P - 1 + 5 - log2 P shuffles
-    // instead of 5 K); lane `l` ends up with the total of type tr_index(l)
-    const int kk = warp_transpose_reduce<P>(v, lane);
-    if (kk >= 0 && kk < K && v[0] != 0.0) atomicAdd(&Jsm[jl * K + kk], v[0]);
+  }
+  if (on) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      if (k < K) {
+        const double v = premul ? w[k] * acc[k] : acc[k];
+        if (v != 0.0) atomicAdd(&out[j * K + k], v);
+      }
+  }
+}
+
+// sumI[k][i] += scale x A_ik sum_{j in the CTA's sample chunk} W_jk X_ji / AW_ij
+// grid = (groups of kMeanThreads genes, sample chunks); thread = one gene
+template <int KP>
+__global__ void __launch_bounds__(kMeanThreads)
+bk_mean_cols_kernel(const float* X, const double* A, const double* W, long long M, int N, int K,
+                    int jchunk, double scale, double* sumI) {
+  extern __shared__ double mean_smem[];  // [jchunk][KP] W rows of the chunk
+  const int tid = threadIdx.x;
+  const long long j0 = (long long)blockIdx.y * jchunk;
+  const int nj = (int)min((long long)jchunk, M - j0);
+  for (int t = tid; t < nj * KP; t += kMeanThreads) {
+    const int jl = t / KP, k = t - jl * KP;
+    mean_smem[t] = k < K ? W[(j0 + jl) * K + k] : 0.0;
   }
   __syncthreads();
-  for (int t = tid; t < nloc * K; t += kBkThreads)
-    if (Jsm[t] != 0.0) atomicAdd(&a.sumJ[j0 * K + t], Jsm[t]);
-  if (in && MODE == 1) {
+  const int i = blockIdx.x * kMeanThreads + tid;
+  if (i >= N) return;
+  double a[KP], acc[KP];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k >= K) break;
-      const double t = accI[k * kBkThreads];
-      if (t != 0.0) atomicAdd(&a.sumI[(size_t)k * N + gi], t * a.scaleI);
+  for (int k = 0; k < KP; ++k) {
+    a[k] = (k < K) ? A[(size_t)k * N + i] : 0.0;
+    acc[k] = 0.0;
+  }
+  const float* xp = X + (size_t)j0 * N + i;
+  float xn[kMeanBatch];
+#pragma unroll
+  for (int q = 0; q < kMeanBatch; ++q) xn[q] = (q < nj) ? __ldg(xp + (size_t)q * N) : 0.f;
+  for (int jb = 0; jb < nj; jb += kMeanBatch) {
+    float xb[kMeanBatch];
+#pragma unroll
+    for (int q = 0; q < kMeanBatch; ++q) {
+      xb[q] = xn[q];
+      const int jq = jb + kMeanBatch + q;
+      xn[q] = (jq < nj) ? __ldg(xp + (size_t)jq * N) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < kMeanBatch; ++q) {
+      if (jb + q >= nj) break;
+      const double* Wj = mean_smem + (jb + q) * KP;
+      double w[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) w[k] = Wj[k];
+      double aw0 = 0.0, aw1 = 0.0;
+#pragma unroll
+      for (int k = 0; k + 1 < KP; k += 2) {
+        aw0 = fma(w[k], a[k], aw0);
+        aw1 = fma(w[k + 1], a[k + 1], aw1);
+      }
+      if (KP & 1) aw0 = fma(w[KP - 1], a[KP - 1], aw0);
+      const double r = (double)xb[q] * rcp_newton(aw0 + aw1);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) acc[k] = fma(w[k], r, acc[k]);
     }
   }
+#pragma unroll
+  for (int k = 0; k < KP; ++k)
+    if (k < K) {
+      const double v = a[k] * acc[k] * scale;
+      if (v != 0.0) atomicAdd(&sumI[(size_t)k * N + i], v);
+    }
 }
 
 // One Gibbs sweep's W step (:140-146) plus the per-sample part of update_suffStats (:69-78).
@@ -279,47 +311,63 @@ __global__ void bk_tail_kernel(const double* eZjk, const double* eLogW, long lon
   }
 }
 
-template <int MODE>
-static void bk_launch_tile(BkShard* b, BkTileArgs& a, cudaStream_t st) {
-  a.X = b->X;
-  a.A = b->A.p;
-  a.W = b->W.p;
-  a.M = b->M;
-  a.N = b->N;
-  a.K = b->K;
-  a.sample_offset = b->sample_offset;
-  const int gx = (b->N + kBkThreads - 1) / kBkThreads;
-  // enough CTAs to fill the machine a few times over; a chunk's W rows and per-sample
-  // sums (2 x chunk x K doubles) get 16 KB next to the per-thread columns (2 x K x T doubles)
-  const long long max_chunk = std::max<long long>(1, (16 * 1024) / (16 * (long long)b->K));
-  long long want_y = std::max<long long>(1, (long long)(8 * b->num_sms + gx - 1) / gx);
-  want_y = std::max<long long>(want_y, (b->M + max_chunk - 1) / max_chunk);
-  long long ny = std::min<long long>(b->M, want_y);
-  a.chunk = (int)((b->M + ny - 1) / ny);
-  ny = (b->M + a.chunk - 1) / a.chunk;
-  URSM_REQUIRE(ny <= 65535, "bulk tile kernel: too many sample chunks");
-  dim3 grid(gx, (unsigned)ny);
-  const int K = b->K;
-  size_t smem = (2 * (size_t)a.chunk * K + 2 * (size_t)K * kBkThreads) * sizeof(double);
-  URSM_REQUIRE(smem <= 200 * 1024, "bulk tile kernel: too many cell types for shared memory");
-#define URSM_TILE_LAUNCH(KM)                                                                    \
-  do {                                                                                          \
-    if (smem > 48 * 1024)                                                                       \
-      URSM_CUDA(cudaFuncSetAttribute(bk_tile_kernel<KM, MODE>,                                  \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    bk_tile_kernel<KM, MODE><<<grid, kBkThreads, smem, st>>>(a);                                \
-  } while (0)
-  if (K <= 4)
-    URSM_TILE_LAUNCH(4);
-  else if (K <= 8)
-    URSM_TILE_LAUNCH(8);
-  else if (K <= 12)
-    URSM_TILE_LAUNCH(12);
-  else if (K <= 20)
-    URSM_TILE_LAUNCH(20);
-  else
-    URSM_TILE_LAUNCH(32);
-#undef URSM_TILE_LAUNCH
+static int bk_mean_kp(int K) {
+  static const int sizes[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
+  for (int v : sizes)
+    if (K <= v) return v;
+  return 32;
+}
+#define URSM_MEAN_DISPATCH(CALL) \
+  switch (bk_mean_kp(K)) {       \
+    case 2: CALL(2); break;      \
+    case 3: CALL(3); break;      \
+    case 4: CALL(4); break;      \
+    case 5: CALL(5); break;      \
+    case 6: CALL(6); break;      \
+    case 8: CALL(8); break;      \
+    case 10: CALL(10); break;    \
+    case 12: CALL(12); break;    \
+    case 16: CALL(16); break;    \
+    case 20: CALL(20); break;    \
+    case 24: CALL(24); break;    \
+    default: CALL(32); break;    \
+  }
+
+// sum_i A_ik X_ji / AW_ij into out[j][k] (times W_jk when `premul`)
+static void bk_launch_mean_rows(BkShard* b, int premul, double* out, cudaStream_t st) {
+  const int K = b->K, N = b->N;
+  const unsigned gy = (unsigned)((b->MpadN + kMeanThreads - 1) / kMeanThreads);
+  // gene chunks: a few waves of CTAs, A rows of a chunk within 32 KB of shared memory
+  const int KP = bk_mean_kp(K);
+  const int max_chunk = std::max(1, (32 * 1024) / (8 * KP));
+  long long gx = std::max<long long>(1, (8LL * b->num_sms + gy - 1) / gy);
+  int gchunk = (int)std::min<long long>(max_chunk, std::max<long long>(16, (N + gx - 1) / gx));
+  gx = (N + gchunk - 1) / gchunk;
+  const size_t smem = (size_t)gchunk * KP * sizeof(double);
+#define URSM_ROWS(KM)                                                                              \
+  bk_mean_rows_kernel<KM><<<dim3((unsigned)gx, gy), kMeanThreads, smem, st>>>(                     \
+      b->XtN.p, b->A.p, b->W.p, b->M, b->MpadN, N, K, gchunk, premul, out)
+  URSM_MEAN_DISPATCH(URSM_ROWS);
+#undef URSM_ROWS
+  URSM_LAUNCH_CHECK();
+}
+
+// scale x A_ik sum_j W_jk X_ji / AW_ij into sumI[k][i]
+static void bk_launch_mean_cols(BkShard* b, double scale, double* sumI, cudaStream_t st) {
+  const int K = b->K, N = b->N;
+  const unsigned gx = (unsigned)((N + kMeanThreads - 1) / kMeanThreads);
+  const int KP = bk_mean_kp(K);
+  const int max_chunk = std::max(1, (32 * 1024) / (8 * KP));
+  long long gy = std::max<long long>(1, (8LL * b->num_sms + gx - 1) / gx);
+  int jchunk = (int)std::min<long long>(max_chunk, std::max<long long>(16, (b->M + gy - 1) / gy));
+  gy = (b->M + jchunk - 1) / jchunk;
+  URSM_REQUIRE(gy <= 65535, "bulk mean kernel: too many sample chunks");
+  const size_t smem = (size_t)jchunk * KP * sizeof(double);
+#define URSM_COLS(KM)                                                                              \
+  bk_mean_cols_kernel<KM><<<dim3(gx, (unsigned)gy), kMeanThreads, smem, st>>>(                     \
+      b->X, b->A.p, b->W.p, b->M, N, K, jchunk, scale, sumI)
+  URSM_MEAN_DISPATCH(URSM_COLS);
+#undef URSM_COLS
   URSM_LAUNCH_CHECK();
 }
 
@@ -419,6 +467,19 @@ static void bk_build_gibbs_inputs(BkShard* b) {
     const long long rows = std::min<long long>(32LL * 32768, b->Mpad - j0);
     bk_transpose_kernel<<<dim3((N + 31) / 32, (unsigned)(rows / 32)), dim3(32, 8)>>>(
         b->X + (size_t)j0 * N, b->M - j0, N, b->Mpad, rank.p, b->Xt.p + j0);
+    URSM_LAUNCH_CHECK();
+  }
+  URSM_CUDA(cudaDeviceSynchronize());
+}
+
+// Input of the mean-mode row pass that never changes during a fit: X gene-major (natural order)
+static void bk_build_mean_inputs(BkShard* b) {
+  b->MpadN = (int)((b->M + 31) / 32) * 32;
+  b->XtN.alloc((size_t)b->N * b->MpadN);
+  for (long long j0 = 0; j0 < b->MpadN; j0 += 32LL * 32768) {
+    const long long rows = std::min<long long>(32LL * 32768, b->MpadN - j0);
+    bk_transpose_kernel<<<dim3((b->N + 31) / 32, (unsigned)(rows / 32)), dim3(32, 8)>>>(
+        b->X + (size_t)j0 * b->N, b->M - j0, b->N, b->MpadN, nullptr, b->XtN.p + j0);
     URSM_LAUNCH_CHECK();
   }
   URSM_CUDA(cudaDeviceSynchronize());
@@ -566,20 +627,16 @@ int ursm_bk_mean_step(ursm_bk* bk, double* d_stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const size_t MK = (size_t)b->M * b->K;
   const unsigned mb = (unsigned)((b->M + 127) / 128), mkb = (unsigned)((MK + 255) / 256);
+  if (!b->XtN.p) bk_build_mean_inputs(b);  // once per fit: the gene-major copy of X
   bk_time_begin(b, st);
   URSM_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)ursm_bk_stats_len(bk) * sizeof(double), st));
   b->acc.zero(st);
   b->eZjk.zero(st);
-  BkTileArgs a;
-  memset(&a, 0, sizeof a);
-  a.sumJ = b->acc.p;
-  bk_launch_tile<0>(b, a, st);
+  bk_launch_mean_rows(b, 0, b->acc.p, st);  // numerators of get_nmf_W
   bk_nmf_update_kernel<<<mb, 128, 0, st>>>(b->W.p, b->acc.p, b->alpha.p, b->M, b->K);
   URSM_LAUNCH_CHECK();
-  a.sumJ = b->eZjk.p;
-  a.sumI = d_stats;
-  a.scaleI = 1.0;
-  bk_launch_tile<1>(b, a, st);
+  bk_launch_mean_rows(b, 1, b->eZjk.p, st);  // E[Z_jk] with the updated W
+  bk_launch_mean_cols(b, 1.0, d_stats, st);  // E[Z_ik]
   bk_mean_finalize_kernel<<<mkb, 256, 0, st>>>(b->W.p, b->eLogW.p, b->eW.p, b->M, b->K);
   URSM_LAUNCH_CHECK();
   bk_tail_kernel<<<1, 1024, 0, st>>>(b->eZjk.p, b->eLogW.p, b->M, b->K,

@@ -53,6 +53,8 @@ struct BkShard {
   const float* X = nullptr;      // [M][N] counts
   DevBuf<float> Xt;              // [N][Mpad] gene-major copy (Gibbs split kernel: lanes = samples)
   int Mpad = 0;                  // M rounded up to a multiple of 32
+  DevBuf<float> XtN;             // [N][MpadN] gene-major copy in the natural gene order (mean-mode row pass)
+  int MpadN = 0;
   DevBuf<float> A32;             // [K][N] fp32 A^T
   DevBuf<float> W32g;            // [ceil(M/32)][K][32] fp32 W of the current sweep
   DevBuf<double> A;              // [K][N] type-major fp64
