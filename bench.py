@@ -59,7 +59,7 @@ UNIT = "updates/s"
 def load_traffic(workload):
     """Measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture,
     committed under profiles/); None when no capture exists for the workload."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         with open(path) as fh:
             ent = json.load(fh).get(workload)
@@ -633,8 +633,12 @@ def gpu_run(args, cfg):
         roofline = {"bound": "hbm", "kernel": "bk_split_kernel (all sweeps)" if args.bulk_mode == "gibbs"
                     else "bk_mean_rows_kernel x2 + bk_mean_cols_kernel (mean update, 3 passes)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel_ms": bk_ms,
-                    "bytes_per_update": 4.0}
+                    "traffic": (load_traffic(args.workload) * passes
+                                if args.bulk_mode == "gibbs" and load_traffic(args.workload) else None),
+                    "peak_source": peak_src, "kernel_ms": bk_ms, "bytes_per_update": 4.0,
+                    "note": ("issue-bound lockstep binomial chains (DESIGN.md 4.2): 79 % of the issue "
+                             "slots busy, X read once per sweep" if args.bulk_mode == "gibbs" else
+                             "bound by the fp64 pipe (DESIGN.md 4.2): fp64 statistics are pinned to 1e-8")}
     cpu = c1 = None
     if world == 1 and not args.no_cpu:
         r = run_cpu_arm(cfg, steps=1, warmup=0, verbose=args.verbose)

@@ -345,9 +345,13 @@ class LogitNormalGibbs_BK(object):
         M, K = self.M, self.K
         if self.iMarkers is not None:
             logging.debug("\t\tZ is initialized with Marker info.")
+            if self.BKexpr is None:
+                raise _lib.UrsmError("marker initialisation needs the host copy of BKexpr "
+                                     "(the marker columns); it was built from device_BK")
             Zjk = np.zeros([M, K])
-            for index in range(self.iMarkers.shape[0]):
-                (i, k) = self.iMarkers[index, :]
+            # the reference ASSIGNS Z[:, i, k] per marker row (:50-51) and then sums over genes:
+            # a (gene, type) pair listed twice counts once
+            for (i, k) in sorted(set((int(r[0]), int(r[1])) for r in np.asarray(self.iMarkers))):
                 Zjk[:, k] += self.BKexpr[:, i] + self.alpha[k]
             W = Zjk.transpose().copy()
             W /= W.sum(axis=0)[np.newaxis, :]
