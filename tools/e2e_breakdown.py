@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--bulk-mode", dest="bulk_mode", default="gibbs")
+    ap.add_argument("--weak", action="store_true",
+                    help="under torchrun: every rank holds the workload's rows (bench.py's e2e arm)")
     args = ap.parse_args()
     cfg = bench.WORKLOADS[args.workload]
     K, N, L, M = cfg["K"], cfg["N"], cfg["L"], cfg["M"]
@@ -49,6 +51,11 @@ def main():
     nY = hY.numpy() if hY is not None else None
     nX = hX.numpy() if hX is not None else None
     init_A = [None]
+    rank = int(os.environ.get("RANK", "0"))
+    shard_kw = {}
+    if args.weak and world > 1:
+        shard_kw = dict(local_rows=True, L_total=L * world, M_total=M * world,
+                        row_offset_SC=rank * L, row_offset_BK=rank * M)
 
     def sync():
         torch.cuda.synchronize()
@@ -60,7 +67,7 @@ def main():
                            sample=cfg["sample"], thin=1,
                            bk_mean_approx=(args.bulk_mode == "mean"), MLE_CONV=1e-6,
                            MLE_maxiter=500, EM_CONV=1e-6, EM_maxiter=10 ** 6, seed=1,
-                           init_A=init_A[0])
+                           init_A=init_A[0], **shard_kw)
         t.append(sync())
         g.init_gibbs()
         t.append(sync())
@@ -81,7 +88,7 @@ def main():
         g.A = g.mle.A
         g.mle.compute_elbo()
         t.append(sync())
-        st = g.gathered_stats()
+        st = g.gathered_stats(local=bool(shard_kw))
         t.append(sync())
         if init_A[0] is None:
             init_A[0] = np.copy(g.init_A)
@@ -106,7 +113,7 @@ def main():
     # ---- steady state: one model, repeated EM iterations (bench.py's device-timed arm)
     g = LogitNormalGEM(BKexpr=nX, SCexpr=nY, K=K, G=G, burnin=cfg["burnin"], sample=cfg["sample"],
                        thin=1, bk_mean_approx=(args.bulk_mode == "mean"), MLE_CONV=1e-6,
-                       MLE_maxiter=500, EM_CONV=1e-6, EM_maxiter=10 ** 6, seed=1)
+                       MLE_maxiter=500, EM_CONV=1e-6, EM_maxiter=10 ** 6, seed=1, **shard_kw)
     g.init_gibbs()
     g.init_mle()
     rows = []

@@ -162,7 +162,7 @@ class PinnedBlock(object):
 
 # read-backs up to this size land in pooled page-locked memory; larger ones use
 # ordinary numpy memory (chunked copies)
-PINNED_READBACK_MAX = 1 << 30
+PINNED_READBACK_MAX = 8 << 30
 
 
 def host_result(shape, dtype=np.float64):

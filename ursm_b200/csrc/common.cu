@@ -62,7 +62,7 @@ static std::mutex g_host_mu;
 static std::multimap<size_t, void*> g_host_free;
 static std::map<void*, size_t> g_host_live;
 static size_t g_host_cached = 0;
-static const size_t kHostCacheCap = (size_t)4 << 30;
+static const size_t kHostCacheCap = (size_t)12 << 30;
 
 void* host_pool_alloc(size_t bytes) {
   {
