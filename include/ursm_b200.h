@@ -235,6 +235,9 @@ int ursm_mle_get_u(ursm_mle* m, double* h_u);
 /* projection onto {y >= min_y, sum y = 1} of a host vector, on the device
  * (utils.py:8-31) -- parity hook for the M-step's inner kernel */
 int ursm_simplex_proj(const double* h_y, int32_t n, double min_y, double* h_out);
+/* the same projection for `rows` vectors of length n stored one after the other (one launch;
+ * gem.py:252-254 projects the K columns of the initial A) */
+int ursm_simplex_proj_rows(const double* h_y, int32_t rows, int32_t n, double min_y, double* h_out);
 
 /* ---- file contract of scUnif.py (:85-94), SURVEY 8f row 1 ---------------------------
  * Headerless comma-separated matrices, byte-compatible with np.savetxt(delimiter=",")

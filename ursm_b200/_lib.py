@@ -80,6 +80,7 @@ SIGNATURES = {
     "ursm_mle_elbo_terms": (c_int, [c_vp, c_vp, c_vp, c_vp]),
     "ursm_mle_get_u": (c_int, [c_vp, c_vp]),
     "ursm_simplex_proj": (c_int, [c_vp, c_i32, c_dbl, c_vp]),
+    "ursm_simplex_proj_rows": (c_int, [c_vp, c_i32, c_i32, c_dbl, c_vp]),
     "ursm_csv_write_f64": (c_int, [ctypes.c_char_p, c_vp, c_i64, c_i64, c_i32]),
     "ursm_csv_shape": (c_int, [ctypes.c_char_p, c_vp, c_vp]),
     "ursm_csv_read_f64": (c_int, [ctypes.c_char_p, c_vp, c_i64, c_i64, c_i32]),

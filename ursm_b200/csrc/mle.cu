@@ -835,6 +835,9 @@ __global__ void mle_epoch_bump_kernel(unsigned long long* epoch, unsigned long l
 __global__ void __launch_bounds__(1024)
 mle_project_kernel(const double* v, double* y, double* out, int N, double m, int normalise) {
   __shared__ double red[96];
+  v += (size_t)blockIdx.x * N;  // one CTA per vector
+  y += (size_t)blockIdx.x * N;
+  out += (size_t)blockIdx.x * N;
   double s = 0.0;
   if (normalise) {
     for (int i = threadIdx.x; i < N; i += blockDim.x) s += v[i];
@@ -1616,19 +1619,24 @@ int ursm_mle_get_u(ursm_mle* mm, double* h_u) {
   URSM_API_END
 }
 
-int ursm_simplex_proj(const double* h_y, int32_t n, double min_y, double* h_out) {
+int ursm_simplex_proj_rows(const double* h_y, int32_t rows, int32_t n, double min_y, double* h_out) {
   URSM_API_BEGIN
-  URSM_REQUIRE(h_y && h_out && n > 0, "ursm_simplex_proj: bad argument");
+  URSM_REQUIRE(h_y && h_out && n > 0 && rows > 0, "ursm_simplex_proj_rows: bad argument");
+  const size_t tot = (size_t)rows * n;
   DevBuf<double> v, y, o;
-  v.alloc(n);
-  y.alloc(n);
-  o.alloc(n);
-  URSM_CUDA(cudaMemcpy(v.p, h_y, n * sizeof(double), cudaMemcpyHostToDevice));
+  v.alloc(tot);
+  y.alloc(tot);
+  o.alloc(tot);
+  URSM_CUDA(cudaMemcpy(v.p, h_y, tot * sizeof(double), cudaMemcpyHostToDevice));
   const int T = std::max(64, std::min(1024, (n + 31) / 32 * 32));
-  mle_project_kernel<<<1, T>>>(v.p, y.p, o.p, n, min_y, 0);
+  mle_project_kernel<<<rows, T>>>(v.p, y.p, o.p, n, min_y, 0);
   URSM_LAUNCH_CHECK();
-  URSM_CUDA(cudaMemcpy(h_out, o.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  URSM_CUDA(cudaMemcpy(h_out, o.p, tot * sizeof(double), cudaMemcpyDeviceToHost));
   URSM_API_END
+}
+
+int ursm_simplex_proj(const double* h_y, int32_t n, double min_y, double* h_out) {
+  return ursm_simplex_proj_rows(h_y, 1, n, min_y, h_out);
 }
 
 }  // extern "C"

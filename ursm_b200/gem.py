@@ -25,7 +25,7 @@ import numpy as np
 from . import dist
 from .e_step_gibbs import LogitNormalGibbs_BK, LogitNormalGibbs_SC
 from .m_step import LogitNormalMLE
-from .utils import simplex_proj
+from .utils import simplex_proj, simplex_proj_columns  # noqa: F401
 
 
 class LogitNormalGEM(object):
@@ -160,8 +160,7 @@ class LogitNormalGEM(object):
             self.init_A = np.zeros([N, K])
             for k in range(K):
                 self.init_A[:, k] = bkmean
-        for k in range(K):
-            self.init_A[:, k] = simplex_proj(self.init_A[:, k], self.min_A)
+        self.init_A = simplex_proj_columns(self.init_A, self.min_A)  # gem.py:252-254, one launch
         self.A = np.copy(self.init_A)
 
     def init_para_SC(self, init_pkappa, init_ptau):
