@@ -99,6 +99,22 @@ int main(int argc, char** argv) {
     for (int k = 0; k < K; ++k) s += (W[j * K + k] = gd(gen));
     for (int k = 0; k < K; ++k) W[j * K + k] /= s;
   }
+  if (const char* e = getenv("PROBE_SORT_SAMPLES")) {
+    // samples with similar mixing weights into the same warp (1: by dominant type, then its weight)
+    std::vector<int> idx(M);
+    for (long long j = 0; j < M; ++j) idx[j] = (int)j;
+    auto key = [&](int j) {
+      int best = 0;
+      for (int k = 1; k < K; ++k)
+        if (W[(size_t)j * K + k] > W[(size_t)j * K + best]) best = k;
+      return std::make_pair(best, W[(size_t)j * K + best]);
+    };
+    if (atoi(e) == 1) std::sort(idx.begin(), idx.end(), [&](int x, int y) { return key(x) < key(y); });
+    std::vector<double> W2(W.size());
+    for (long long j = 0; j < M; ++j)
+      for (int k = 0; k < K; ++k) W2[j * K + k] = W[(size_t)idx[j] * K + k];
+    W = W2;
+  }
   const int ngroups = (int)((M + 31) / 32), Mpad = ngroups * 32;
   std::vector<float> Xt((size_t)N * Mpad, 0.f), A32((size_t)K * N), W32g((size_t)ngroups * K * 32, 0.f);
   for (size_t t = 0; t < A32.size(); ++t) A32[t] = (float)A[t];

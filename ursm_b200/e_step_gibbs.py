@@ -419,6 +419,10 @@ class LogitNormalGibbs_BK(object):
         st["_ursm_bk"] = weakref.ref(self)
         st["_ursm_bk_tail"] = host[N * K:N * K + K + 1].copy()  # sum_j E log W_k | sum Zjk*logW
         if host[N * K + K + 1] != 0:
-            raise _lib.UrsmError("bulk Gibbs kernels: %d gamma draws ran out of attempts"
-                                 % int(host[N * K + K + 1]))
+            # (the cold kernel adds 1 << 20 per sweep whose hand-over list did not fit, the
+            # Dirichlet kernel 1 per gamma draw that ran out of attempts; neither has been seen)
+            bad = int(host[N * K + K + 1])
+            raise _lib.UrsmError("bulk Gibbs kernels: %d sweeps overflowed the hand-over list of the "
+                                 "split kernel, %d gamma draws ran out of attempts"
+                                 % (bad >> 20, bad & ((1 << 20) - 1)))
         self._suff = st
