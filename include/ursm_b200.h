@@ -250,6 +250,25 @@ int ursm_csv_write_f64(const char* path, const double* data, int64_t rows, int64
 int ursm_csv_shape(const char* path, int64_t* rows, int64_t* cols);
 int ursm_csv_read_f64(const char* path, double* out, int64_t rows, int64_t cols, int32_t nthreads);
 
+/* ---- synthetic inputs on the device --------------------------------------
+ * The distributions of the reference's demo generator, demo/demo_simulate_data.py:
+ * ursm_synth_bulk   simulate_bulk :45-69 with depths ~ Poisson(depth_per_gene * N) (:150-152):
+ *                   W_j ~ Dir(alpha), X_j ~ Mult(depth_j, A W_j); d_X [M][N] fp32 on the device,
+ *                   h_W [M][K] (may be null)
+ * ursm_synth_cells  simulate_sc :72-114 with depths ~ Poisson(depth_per_gene * N): kappa_l ~
+ *                   N(kappa, kappa_sd), tau_l ~ N(tau_scale N, tau_sd_frac tau_scale N),
+ *                   S_li ~ Bern(expit(kappa_l + tau_l A[i, G_l])), Y_l ~ Mult(depth_l,
+ *                   normalise(A[:, G_l] S_l)); d_Y [L][N] fp32, d_S [L][N] bytes on the device
+ * A multinomial with a Poisson total is drawn as independent Poissons (the same joint law).
+ * Streams are keyed on (seed, gene, row_offset + row): a shard of rows does not depend on who
+ * draws it.  h_A is N x K row-major. */
+int ursm_synth_bulk(const double* h_A, int32_t N, int32_t K, int64_t M, const double* h_alpha,
+                    double depth_per_gene, uint64_t seed, int64_t row_offset, float* d_X, double* h_W);
+int ursm_synth_cells(const double* h_A, int32_t N, int32_t K, const int64_t* h_G, int64_t L,
+                     uint64_t seed, int64_t row_offset, double depth_per_gene, double kappa,
+                     double kappa_sd, double tau_scale, double tau_sd_frac, float* d_Y, uint8_t* d_S,
+                     double* h_kappa, double* h_tau);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,9 @@ SIGNATURES = {
     "ursm_mle_get_u": (c_int, [c_vp, c_vp]),
     "ursm_simplex_proj": (c_int, [c_vp, c_i32, c_dbl, c_vp]),
     "ursm_simplex_proj_rows": (c_int, [c_vp, c_i32, c_i32, c_dbl, c_vp]),
+    "ursm_synth_bulk": (c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_dbl, c_u64, c_i64, c_vp, c_vp]),
+    "ursm_synth_cells": (c_int, [c_vp, c_i32, c_i32, c_vp, c_i64, c_u64, c_i64, c_dbl, c_dbl, c_dbl,
+                                 c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]),
     "ursm_csv_write_f64": (c_int, [ctypes.c_char_p, c_vp, c_i64, c_i64, c_i32]),
     "ursm_csv_shape": (c_int, [ctypes.c_char_p, c_vp, c_vp]),
     "ursm_csv_read_f64": (c_int, [ctypes.c_char_p, c_vp, c_i64, c_i64, c_i32]),

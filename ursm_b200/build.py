@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libursm_b200.so")
-SOURCES = ["common.cu", "sc_gibbs.cu", "bk_gibbs.cu", "mle.cu", "csv_io.cpp"]
+SOURCES = ["common.cu", "sc_gibbs.cu", "bk_gibbs.cu", "mle.cu", "synth.cu", "csv_io.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-rdc=false"]
 
