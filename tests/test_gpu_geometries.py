@@ -42,7 +42,8 @@ def _itype(G, K):
 
 def _setenv(monkeypatch, env):
     for k in ("URSM_SC_ACC_SMEM_LIMIT", "URSM_SC_ACC_RED", "URSM_SC_GRID", "URSM_SC_MAX_THREADS",
-              "URSM_SC_GENES_PER_THREAD", "URSM_MLE_Y_SMEM", "URSM_SC_STATE_GLOBAL", "URSM_MLE_FUSED"):
+              "URSM_SC_GENES_PER_THREAD", "URSM_MLE_Y_SMEM", "URSM_SC_STATE_GLOBAL", "URSM_MLE_FUSED",
+              "URSM_MLE_FUSED_SMALL", "URSM_MLE_FUSED_SMALL_CTAS"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -327,17 +328,24 @@ def test_single_cell_chain_matches_reference_chain_variants(variant, golden, mon
 # ---------------------------------------------------------------------------
 # M-step at the production gene counts against the oracle (injected states)
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["c2", "c3", "c3_yglobal", "ragged"])
+@pytest.mark.parametrize("case", ["c2", "c3", "c3_yglobal", "ragged", "c5", "c5_general", "c5_u16"])
 def test_mstep_production_shapes_match_oracle(case, monkeypatch):
     """N = 5,000: two gene segments in `mle_u_kernel`, column sums over several CTAs;
     N = 20,000: five segments, the trial column of `mle_cand_kernel` in 160 KB of shared
     memory -- or in global memory (`c3_yglobal`); `ragged`: N not a multiple of 8, so the
-    scalar-load paths of both streaming kernels; sample = 300 -> 16-bit counters."""
+    scalar-load paths of both streaming kernels; sample = 300 -> 16-bit counters;
+    N = 2,000 with K = 20 (`c5`): the persistent short-row pass `mle_pass_fused_small_kernel`,
+    21 blocks and ~3 type runs per CTA (seven CTAs forced), the general fused
+    kernel on the same input (`c5_general`), and 16-bit counters at N = 1,000 (`c5_u16`)."""
     import ursm_b200.e_step_gibbs as es
     import ursm_b200.m_step as ms
-    _setenv(monkeypatch, {"URSM_MLE_Y_SMEM": "0"} if case == "c3_yglobal" else {})
+    _setenv(monkeypatch, {"URSM_MLE_Y_SMEM": "0"} if case == "c3_yglobal" else
+            ({"URSM_MLE_FUSED_SMALL": "0"} if case == "c5_general" else
+             ({"URSM_MLE_FUSED_SMALL_CTAS": "7"} if case == "c5" else {})))
     N, K, L, M, T = {"c2": (5000, 5, 60, 8, 3), "c3": (20000, 10, 40, 6, 2),
-                     "c3_yglobal": (20000, 10, 30, 0, 2), "ragged": (4801, 4, 50, 5, 300)}[case]
+                     "c3_yglobal": (20000, 10, 30, 0, 2), "ragged": (4801, 4, 50, 5, 300),
+                     "c5": (2000, 20, 2600, 0, 3), "c5_general": (2000, 20, 2600, 0, 3),
+                     "c5_u16": (1000, 6, 1500, 0, 300)}[case]
     sim, Y, G, itype, A, pk, pt = _problem(N, K, L, seed=15, M=M)
     X = sim["X"] if M else None
     al = np.ones(K)

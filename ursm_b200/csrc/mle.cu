@@ -431,6 +431,127 @@ mle_pass_fused_kernel(const CT* cnt, const int* order, const int* type_start, co
   }
 }
 
+// The same pass for SHORT gene vectors (at most 256 eight-byte groups per row: N <= 2048 with
+// byte counters, the c5 shape), where the kernel above leaves half of its 512 threads without a
+// group.  256 threads, one warp per row, thread t owns group t; PERSISTENT CTAs: a CTA walks a
+// contiguous range of the type-sorted cells in blocks of `nc` rows and keeps (a) the column
+// A[:, type] staged in shared memory and (b) its column sums in registers for as long as the type
+// does not change -- one fp64 atomic per gene, CTA and run instead of one per block (at c5 the
+// atomics of 2,451 blocks x 2,000 genes were a cost of their own).
+constexpr int kSmallThreads = 256;
+
+template <class CT>
+__global__ void __launch_bounds__(kSmallThreads, 4)
+mle_pass_fused_small_kernel(const CT* cnt, const int* order, const int* type_start, const double* A,
+                            const int* active, const double* R, double* u, long long L, int N, int K,
+                            int nc, long long cells_per_cta, double inv_sample, double* out) {
+  constexpr int C8 = 8 / (int)sizeof(CT);
+  constexpr int NW = kSmallThreads / 32;
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t row_bytes = (size_t)N * sizeof(CT);
+  const int nv = (int)(row_bytes >> 3);  // <= 256 (host checks)
+  double* w_s = reinterpret_cast<double*>(fused_smem);   // [nc] R_l / u_l / sample
+  double* dot_s = w_s + nc;                               // [nc] row dot products
+  double* A_s = reinterpret_cast<double*>(fused_smem + (((size_t)nc * 16 + 15) & ~(size_t)15));  // [N]
+  unsigned char* rows = reinterpret_cast<unsigned char*>(A_s + N);  // [nc][row_bytes]
+  const long long cta_lo = (long long)blockIdx.x * cells_per_cta;
+  const long long cta_hi = min(L, cta_lo + cells_per_cta);
+  const bool own = tid < nv;
+  double acc[C8];
+#pragma unroll
+  for (int q = 0; q < C8; ++q) acc[q] = 0.0;
+  int cur = -1;  // type whose column is staged and whose sums are in `acc`
+  int k0 = 0;    // first type that can still have cells at or after the block in hand
+  for (long long blk_lo = cta_lo; blk_lo < cta_hi; blk_lo += nc) {
+    const long long blk_hi = min(cta_hi, blk_lo + nc);
+    while (k0 < K - 1 && (long long)type_start[k0 + 1] <= blk_lo) ++k0;
+    for (int k = k0; k < K && (long long)type_start[k] < blk_hi; ++k) {
+      const long long lo = max(blk_lo, (long long)type_start[k]);
+      const long long hi = min(blk_hi, (long long)type_start[k + 1]);
+      if (lo >= hi || !active[k]) continue;
+      if (k != cur) {
+        if (cur >= 0 && own) {
+          double* o = out + (size_t)cur * N + (size_t)tid * C8;
+#pragma unroll
+          for (int q = 0; q < C8; ++q) {
+            if (acc[q] != 0.0) atomicAdd(o + q, acc[q]);
+            acc[q] = 0.0;
+          }
+        }
+        cur = k;
+        __syncthreads();  // readers of the previous column are done
+        // the column as C8/2 arrays of pairs, pair q of group v at [q][v]: the lanes of a warp
+        // (consecutive v) then read consecutive 16 bytes -- conflict free
+        const double2* src = reinterpret_cast<const double2*>(A + (size_t)k * N);
+        double2* dst = reinterpret_cast<double2*>(A_s);
+        for (int j = tid; j < N / 2; j += kSmallThreads) {
+          const int v = j / (C8 / 2), q = j - v * (C8 / 2);
+          dst[q * nv + v] = src[j];
+        }
+      }
+      __syncthreads();  // column staged; the previous run's rows / weights are no longer read
+      // ---- (1) stage the rows, row dots: one warp per row, eight 8-byte loads in flight per lane
+      for (long long c = lo + warp; c < hi; c += NW) {
+        const int l = order[c];
+        const uint2* src = reinterpret_cast<const uint2*>(cnt + (size_t)l * N);
+        uint2* dst = reinterpret_cast<uint2*>(rows + (size_t)(c - blk_lo) * row_bytes);
+        uint2 x[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const int v = lane + 32 * h;
+          x[h] = v < nv ? src[v] : make_uint2(0u, 0u);
+        }
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const int v = lane + 32 * h;
+          if (v < nv) {
+            dst[v] = x[h];
+            double e[C8];
+            CntVec<CT>::unpack(x[h], e);
+            const double2* a2 = reinterpret_cast<const double2*>(A_s) + v;
+#pragma unroll
+            for (int q = 0; q < C8 / 2; ++q) {
+              const double2 p = a2[q * nv];
+              d0 = fma(p.x, e[2 * q], d0);
+              d1 = fma(p.y, e[2 * q + 1], d1);
+            }
+          }
+        }
+        const double d = warp_sum(d0 + d1);
+        if (lane == 0) dot_s[c - blk_lo] = d;
+      }
+      __syncthreads();
+      for (long long c = lo + tid; c < hi; c += kSmallThreads) {
+        const int l = order[c];
+        const double ul = dot_s[c - blk_lo] * inv_sample;
+        u[l] = ul;
+        w_s[c - blk_lo] = (R[l] / ul) * inv_sample;
+      }
+      __syncthreads();
+      // ---- (2) weighted column sums of the staged rows, into the thread's registers
+      if (own) {
+        const unsigned char* col = rows + (size_t)tid * 8;
+        for (long long c = lo; c < hi; ++c) {
+          const uint2 v = *reinterpret_cast<const uint2*>(col + (size_t)(c - blk_lo) * row_bytes);
+          const double w = w_s[c - blk_lo];
+          double e[C8];
+          CntVec<CT>::unpack(v, e);
+#pragma unroll
+          for (int q = 0; q < C8; ++q) acc[q] = fma(e[q], w, acc[q]);
+        }
+      }
+    }
+  }
+  if (cur >= 0 && own) {
+    double* o = out + (size_t)cur * N + (size_t)tid * C8;
+#pragma unroll
+    for (int q = 0; q < C8; ++q)
+      if (acc[q] != 0.0) atomicAdd(o + q, acc[q]);
+  }
+}
+
 // out[type] = sum_{l in type} R_l log u_l   (compute_elbo :308), every type
 __global__ void mle_rlogu_kernel(const int* G, const double* R, const double* u, long long L,
                                  double* out) {
@@ -1007,6 +1128,15 @@ static bool mle_fused_ok(const Mle* m) {
   return (row_bytes % 8) == 0 && (m->N % 2) == 0 && m->N <= 8192;
 }
 
+// short rows (at most 256 eight-byte groups): the persistent 256-thread kernel
+// (URSM_MLE_FUSED_SMALL=0 keeps the general one: tests)
+static bool mle_fused_small_ok(const Mle* m) {
+  if (const char* e = getenv("URSM_MLE_FUSED_SMALL"))
+    if (!atoi(e)) return false;
+  const size_t row_bytes = (size_t)m->N * m->sc->cnt_w;
+  return row_bytes / 8 <= 256 && (size_t)m->N * sizeof(double) + 4 * (row_bytes + 16) + 64 <= 54 * 1024;
+}
+
 static void mle_fused_geometry(const Mle* m, int* nc_out, size_t* smem_out) {
   const size_t row_bytes = (size_t)m->N * m->sc->cnt_w;
   const long long cap = std::max<long long>(1, (long long)(100 * 1024) / (long long)row_bytes);
@@ -1040,6 +1170,43 @@ static void mle_pass(Mle* m, double* d_part, cudaStream_t st, bool lean = false)
   if (!lean) URSM_CUDA(cudaMemsetAsync(d_part, 0, (KN + m->K) * sizeof(double), st));
   const double inv = 1.0 / s->sample;
   URSM_REQUIRE(s->cnt_w > 0, "M-step: the single-cell E-step has not run yet");
+  if (mle_fused_ok(m) && mle_fused_small_ok(m)) {
+    // short gene vectors: persistent CTAs, four per SM; A column + a block of rows in shared memory
+    const size_t row_bytes = (size_t)m->N * s->cnt_w;
+    const size_t budget = 54 * 1024;
+    const size_t a_bytes = (size_t)m->N * sizeof(double);
+    long long nc = std::max<long long>(1, ((long long)budget - (long long)a_bytes - 64) / (long long)(row_bytes + 16));
+    nc = std::min<long long>(nc, 64);
+    long long slots = 4LL * m->num_sms;
+    if (const char* e = getenv("URSM_MLE_FUSED_SMALL_CTAS"))  // tests: many blocks and runs per CTA
+      slots = std::max(1, atoi(e));
+    long long per = (s->L + slots - 1) / slots;
+    per = std::max<long long>(nc, (per + nc - 1) / nc * nc);  // whole blocks per CTA
+    const unsigned nb = (unsigned)((s->L + per - 1) / per);
+    const size_t smem = ((((size_t)nc * 16 + 15) & ~(size_t)15)) + a_bytes + (size_t)nc * row_bytes;
+    static bool configured = false;
+    if (!configured) {
+      URSM_CUDA(cudaFuncSetAttribute(mle_pass_fused_small_kernel<unsigned char>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      URSM_CUDA(cudaFuncSetAttribute(mle_pass_fused_small_kernel<unsigned short>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      configured = true;
+    }
+    if (s->cnt_w == 1)
+      mle_pass_fused_small_kernel<unsigned char><<<nb, kSmallThreads, smem, st>>>(
+          s->cnt.p, s->order.p, m->type_start.p, m->A.p, m->act_cur.p, s->R.p, m->u.p, s->L, m->N,
+          m->K, (int)nc, per, inv, d_part);
+    else
+      mle_pass_fused_small_kernel<unsigned short><<<nb, kSmallThreads, smem, st>>>(
+          reinterpret_cast<const unsigned short*>(s->cnt.p), s->order.p, m->type_start.p, m->A.p,
+          m->act_cur.p, s->R.p, m->u.p, s->L, m->N, m->K, (int)nc, per, inv, d_part);
+    URSM_LAUNCH_CHECK();
+    if (lean) return;
+    mle_rlogu_kernel<<<(unsigned)((s->L + 255) / 256), 256, 0, st>>>(s->G.p, s->R.p, m->u.p, s->L,
+                                                                    d_part + KN);
+    URSM_LAUNCH_CHECK();
+    return;
+  }
   if (mle_fused_ok(m)) {
     int nc;
     size_t smem;
