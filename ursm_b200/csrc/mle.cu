@@ -354,13 +354,25 @@ mle_pass_fused_kernel(const CT* cnt, const int* order, const int* type_start, co
   const size_t row_bytes = (size_t)N * sizeof(CT);  // a multiple of 8, N even (host checks)
   double* w_s = reinterpret_cast<double*>(fused_smem);           // [nc] R_l / u_l / sample
   double* dot_s = w_s + nc;                                       // [nc][2] half-row dot products
-  unsigned char* rows = fused_smem + (((size_t)nc * 24 + 15) & ~(size_t)15);  // [nc][row_bytes]
+  double2* A_s = reinterpret_cast<double2*>(fused_smem + (((size_t)nc * 24 + 15) & ~(size_t)15));  // [C8/2][nv]
+  unsigned char* rows = reinterpret_cast<unsigned char*>(A_s + N / 2);  // [nc][row_bytes]
   const long long c_lo = (long long)blockIdx.x * nc, c_hi = min(L, c_lo + nc);
+  const int nvA = (int)(row_bytes >> 3);
   for (int k = 0; k < K; ++k) {
     const long long lo = max(c_lo, (long long)type_start[k]);
     const long long hi = min(c_hi, (long long)type_start[k + 1]);
     if (lo >= hi || !active[k]) continue;
-    const double* Ak = A + (size_t)k * N;
+    {
+      // the column A[:, k] as C8/2 arrays of pairs (pair q of group v at [q][v]): consecutive
+      // lanes read consecutive 16 bytes in the dot below -- conflict free, and no global load
+      // sits between the counter loads and their use
+      const double2* src = reinterpret_cast<const double2*>(A + (size_t)k * N);
+      for (int j = tid; j < N / 2; j += kFusedThreads) {
+        const int v = j / (C8 / 2), q = j - v * (C8 / 2);
+        A_s[q * nvA + v] = src[j];
+      }
+      __syncthreads();
+    }
     // ---- phase 1: stage the rows, row dots.  Two warps per row (interleaved 8-byte loads,
     // eight in flight per lane: the pass is a chain of memory round trips, not arithmetic)
     for (long long cb = lo; cb < hi; cb += nwarp / 2) {
@@ -371,7 +383,7 @@ mle_pass_fused_kernel(const CT* cnt, const int* order, const int* type_start, co
         const uint2* src = reinterpret_cast<const uint2*>(cnt + (size_t)l * N);
         uint2* dst = reinterpret_cast<uint2*>(rows + (size_t)(c - c_lo) * row_bytes);
         const int nv = (int)(row_bytes >> 3);
-        double acc = 0.0;
+        double acc = 0.0, acc2 = 0.0;
         for (int v0 = half * 32 + lane; v0 < nv; v0 += 64 * 8) {
           uint2 x[8];
 #pragma unroll
@@ -386,16 +398,15 @@ mle_pass_fused_kernel(const CT* cnt, const int* order, const int* type_start, co
             dst[v] = x[h];
             double e[C8];
             CntVec<CT>::unpack(x[h], e);
-            const double2* a2 = reinterpret_cast<const double2*>(Ak + (size_t)v * C8);
 #pragma unroll
             for (int q = 0; q < C8 / 2; ++q) {
-              const double2 p = a2[q];
+              const double2 p = A_s[q * nvA + v];
               acc = fma(p.x, e[2 * q], acc);
-              acc = fma(p.y, e[2 * q + 1], acc);
+              acc2 = fma(p.y, e[2 * q + 1], acc2);
             }
           }
         }
-        acc = warp_sum(acc);
+        acc = warp_sum(acc + acc2);
         if (lane == 0) dot_s[2 * (c - c_lo) + half] = acc;
       }
     }
@@ -1139,13 +1150,15 @@ static bool mle_fused_small_ok(const Mle* m) {
 
 static void mle_fused_geometry(const Mle* m, int* nc_out, size_t* smem_out) {
   const size_t row_bytes = (size_t)m->N * m->sc->cnt_w;
-  const long long cap = std::max<long long>(1, (long long)(100 * 1024) / (long long)row_bytes);
+  const size_t a_bytes = (size_t)m->N * sizeof(double);  // the staged column A[:, type]
+  const long long cap = std::max<long long>(
+      1, ((long long)(108 * 1024) - (long long)a_bytes) / (long long)row_bytes);
   int per_sm = 2;  // CTAs per SM the grid aims at: their phases overlap
   if (const char* e = getenv("URSM_MLE_FUSED_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
   const long long slots = (long long)per_sm * m->num_sms;
   long long nc = (m->sc->L + slots - 1) / slots;
   nc = std::max<long long>(std::min<long long>(nc, cap), std::min<long long>(8, cap));
-  const size_t smem = (((size_t)nc * 24 + 15) & ~(size_t)15) + (size_t)nc * row_bytes;
+  const size_t smem = (((size_t)nc * 24 + 15) & ~(size_t)15) + a_bytes + (size_t)nc * row_bytes;
   static size_t configured[2] = {0, 0};
   const int which = m->sc->cnt_w == 1 ? 0 : 1;
   if (smem > 48 * 1024 && smem > configured[which]) {
