@@ -440,3 +440,36 @@ def test_bulk_split_moments_K10(depth, split, monkeypatch):
         assert abs(np.mean(z)) < 5.0 / np.sqrt(z.size)
     np.testing.assert_allclose(bk.suff_stats["exp_Zjk"].sum(axis=1), X.sum(axis=1), rtol=1e-12)
     np.testing.assert_allclose(bk.suff_stats["exp_Zik"].sum(axis=1), X.sum(axis=0), rtol=1e-12)
+
+
+@pytest.mark.parametrize("depth", [30.0, 400.0, 2500.0])
+def test_bulk_split_does_not_depend_on_the_grouping_of_samples(depth, monkeypatch):
+    """A draw of the lockstep split kernel depends on its own (gene, global sample) only: not on
+    which 31 other samples share its warp, not on the order the genes are dealt in (each shard
+    sorts them by ITS column sums), not on which search the neighbours need.  Shards that cut the
+    samples at positions that are not multiples of 32 must reproduce the unsharded chain --
+    in all three binomial regimes (depth 2500: through the hand-over list)."""
+    import ursm_b200.e_step_gibbs as es
+    monkeypatch.setenv("URSM_BK_SPLIT", "lockstep")
+    rs = np.random.RandomState(8)
+    M, N, K = 83, 160, 4
+    A = rs.dirichlet(np.ones(N) * 0.6, K).T
+    A = np.maximum(A, 1e-6)
+    A /= A.sum(axis=0)
+    W = rs.dirichlet(np.ones(K) * 1.5, M)
+    X = rs.poisson(depth * N * W.dot(A.T)).astype(float)
+    al = np.ones(K)
+    full = es.LogitNormalGibbs_BK(A, al, X, seed=31)
+    full.init_gibbs()
+    full.gibbs(burnin=3, sample=6, thin=1, mean_approx=False)
+    zik, eW, eZjk = 0, [], []
+    for lo, hi in ((0, 21), (21, 58), (58, M)):
+        p = es.LogitNormalGibbs_BK(A, al, X[lo:hi], row_offset=lo, total_rows=M, seed=31)
+        p.init_gibbs()
+        p.gibbs(burnin=3, sample=6, thin=1, mean_approx=False)
+        zik = zik + p.suff_stats["exp_Zik"]
+        eW.append(p.suff_stats["exp_W"])
+        eZjk.append(p.suff_stats["exp_Zjk"])
+    np.testing.assert_allclose(zik, full.suff_stats["exp_Zik"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(np.hstack(eW), full.suff_stats["exp_W"], rtol=1e-12)
+    np.testing.assert_allclose(np.vstack(eZjk), full.suff_stats["exp_Zjk"], rtol=1e-12)
