@@ -590,6 +590,17 @@ def gpu_run(args, cfg):
                 ent["e2e_h2d_bytes_per_step"] = r["e2e"]["h2d_bytes_per_step"]
                 ent["e2e_d2h_bytes_per_step"] = r["e2e"]["d2h_bytes_per_step"]
             north[wl] = ent
+        # the command line's DEFAULT bulk mode (one deterministic mean update per EM
+        # iteration instead of the Gibbs sweeps) on the headline workload, for comparison
+        import copy
+        margs = copy.copy(args)
+        margs.bulk_mode = "mean"
+        r = run_workload("c2", WORKLOADS["c2"], margs, 5, 2, world, rank, flush, False, 1)
+        north["c2_bulk_mean_approx"] = {
+            "desc": WORKLOADS["c2"]["desc"] + "; bulk E-step = mean update (CLI default)",
+            "s_per_em_iter": r["s_per_em_iter"], "value": r["value"], "unit": UNIT,
+            "estep_ms": r["estep_ms"], "mstep_ms": r["mstep_ms"], "kernel_ms": r["kernel_ms"],
+            "updates_per_step_per_gpu": r["updates_per_step_per_gpu"]}
         if world == 8:
             north["target"] = {"what": "c3 on 8 x B200: one EM iteration (100 Gibbs samples) < 1 s",
                                "s_per_em_iter": north["c3"]["s_per_em_iter"],
