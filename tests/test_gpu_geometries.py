@@ -473,3 +473,35 @@ def test_bulk_split_does_not_depend_on_the_grouping_of_samples(depth, monkeypatc
     np.testing.assert_allclose(zik, full.suff_stats["exp_Zik"], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(np.hstack(eW), full.suff_stats["exp_W"], rtol=1e-12)
     np.testing.assert_allclose(np.vstack(eZjk), full.suff_stats["exp_Zjk"], rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# bulk mean mode: every padded-K instantiation of the streaming passes, ragged shapes
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("K,M,N", [(2, 37, 130), (3, 5, 1031), (5, 70, 257), (7, 130, 64), (9, 33, 300),
+                                   (11, 40, 129), (13, 260, 50), (17, 9, 400), (21, 64, 96), (27, 31, 200),
+                                   (32, 20, 150)])
+def test_bulk_mean_step_all_type_counts(K, M, N):
+    """get_nmf_W (:157-164) + draw_Z_mean (:149-155) + update_suffStats (:69-78) against the
+    oracle for type counts that land in each padded instantiation (KP = 2, 3, 5, 8, 10, 12, 16,
+    20, 24, 32, 32), sample / gene counts that are not multiples of the CTA tiles, zero counts and
+    several consecutive mean updates (the W state persists)."""
+    import ursm_b200.e_step_gibbs as es
+    rs = np.random.RandomState(K * 1000 + M)
+    A = rs.dirichlet(np.ones(N) * 0.8, K).T
+    A = np.maximum(A, 1e-6)
+    A /= A.sum(axis=0)
+    W = rs.dirichlet(np.ones(K) * 1.5, M)
+    X = rs.poisson(40.0 * N * W.dot(A.T)).astype(float)
+    X[rs.rand(M, N) < 0.2] = 0.0
+    al = 1.0 + rs.rand(K)
+    bk = es.LogitNormalGibbs_BK(A, al, X)
+    obk = orc.OracleGibbsBK(A, al, X)
+    bk.init_gibbs()
+    obk.init_gibbs()
+    for it in range(3):
+        bk.gibbs(mean_approx=True)
+        obk.gibbs(mean_approx=True)
+        for key in ("exp_W", "exp_logW", "exp_Zik", "exp_Zjk"):
+            np.testing.assert_allclose(bk.suff_stats[key], obk.suff_stats[key], rtol=1e-9, atol=1e-9,
+                                       err_msg="%s after update %d" % (key, it))
