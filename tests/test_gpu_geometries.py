@@ -505,3 +505,36 @@ def test_bulk_mean_step_all_type_counts(K, M, N):
         for key in ("exp_W", "exp_logW", "exp_Zik", "exp_Zjk"):
             np.testing.assert_allclose(bk.suff_stats[key], obk.suff_stats[key], rtol=1e-9, atol=1e-9,
                                        err_msg="%s after update %d" % (key, it))
+
+
+@pytest.mark.parametrize("split", ["lockstep", "lane"])
+@pytest.mark.parametrize("K,M,N", [(1, 5, 40), (2, 1, 7), (2, 33, 1), (32, 40, 64), (6, 65, 333)])
+def test_bulk_split_edge_shapes(K, M, N, split, monkeypatch):
+    """The Gibbs split at the edges of its geometry: one type (everything goes to it), one
+    sample, one gene, the maximum type count, sample counts one past a warp: exact invariants of
+    a multinomial split on every retained sweep, and first moments within Monte-Carlo error."""
+    import ursm_b200.e_step_gibbs as es
+    monkeypatch.setenv("URSM_BK_SPLIT", split)
+    rs = np.random.RandomState(K + 7 * M + 13 * N)
+    A = rs.dirichlet(np.ones(N), K).T if N > 1 else np.ones((1, K))
+    A = np.maximum(A, 1e-6)
+    A /= A.sum(axis=0)
+    W = rs.dirichlet(np.ones(K) * 1.5, M)
+    X = rs.poisson(60.0 * N * W.dot(A.T)).astype(float)
+    bk = es.LogitNormalGibbs_BK(A, np.ones(K), X, seed=5)
+    bk.set_state(W.T.copy())
+    bk.freeze = 1
+    S = 200
+    bk.gibbs(burnin=0, sample=S, thin=1, mean_approx=False)
+    np.testing.assert_allclose(bk.suff_stats["exp_Zjk"].sum(axis=1), X.sum(axis=1), rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(bk.suff_stats["exp_Zik"].sum(axis=1), X.sum(axis=0), rtol=1e-12, atol=1e-9)
+    AW = A.dot(W.T)
+    P = (A[None, :, :] * W[:, None, :]) / AW.T[:, :, None]
+    EZ, VZ = X[:, :, None] * P, X[:, :, None] * P * (1 - P)
+    for got, ax in ((bk.suff_stats["exp_Zik"], 0), (bk.suff_stats["exp_Zjk"], 1)):
+        sd = np.sqrt(VZ.sum(axis=ax) / S)
+        ok = sd > 0
+        if ok.any():
+            z = ((got - EZ.sum(axis=ax))[ok] / sd[ok]).ravel()
+            assert np.abs(z).max() < 5.5, np.abs(z).max()
+        np.testing.assert_allclose(got[~ok], EZ.sum(axis=ax)[~ok], rtol=1e-12, atol=1e-9)
