@@ -88,3 +88,30 @@ def test_device_generator_matches_reference_generator(golden):
     Y2 = synth.cells_on_device(A, G[:64], seed=3, row_offset=0)[0].double().cpu().numpy()
     np.testing.assert_array_equal(Y2, synth.cells_on_device(A, G[:64], seed=3, row_offset=0)[0]
                                   .double().cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_device_generator_degenerate_cells():
+    """Every cell gets at least one read (the reference divides by the depth, m_step.py:125): cells
+    whose Poisson draws all came up zero get one read on their most probable gene, cells without
+    any expressed gene fall back to the profile itself; shards of rows do not depend on who draws
+    them (row_offset keys the streams)."""
+    from ursm_b200 import synth
+    A = synth.profile_matrix(64, 3, seed=1)
+    G = (np.arange(300) % 3).astype(np.int64)
+    Y, S, kap, tau = synth.cells_on_device(A, G, seed=2, sc_depth=0.002)      # ~0.13 reads per cell
+    Y, S = Y.double().cpu().numpy(), S.cpu().numpy()
+    assert np.all(Y.sum(axis=1) >= 1) and (Y.sum(axis=1) == 1).mean() > 0.7
+    one = Y.sum(axis=1) == 1
+    empty_fill = one & (S.sum(axis=1) > 0)
+    # the filled read sits on an expressed gene
+    assert np.all((Y[empty_fill] > 0) <= (S[empty_fill] > 0))
+    Yd, Sd, _, _ = synth.cells_on_device(A, G, seed=2, kappa=-60.0, kappa_sd=0.0, tau_scale=0.0)
+    assert Sd.sum().item() == 0 and np.all(Yd.double().cpu().numpy().sum(axis=1) >= 1)
+    # rows 100..199 drawn as their own shard equal rows 100..199 of the whole
+    Y2 = synth.cells_on_device(A, G[100:200], seed=2, sc_depth=0.002, row_offset=100)[0]
+    np.testing.assert_array_equal(Y2.double().cpu().numpy(), Y[100:200])
+    X, W = synth.bulk_on_device(A, 40, seed=2)
+    X2, W2 = synth.bulk_on_device(A, 15, seed=2, row_offset=25)
+    np.testing.assert_array_equal(X2.cpu().numpy(), X[25:40].cpu().numpy())
+    np.testing.assert_array_equal(W2, W[25:40])
