@@ -91,6 +91,13 @@ rs = np.random.RandomState(0)
 S = rs.rand(11, 5)
 part = S[lo:hi].sum(axis=0)
 assert np.allclose(dist.all_reduce_np(part), S.sum(axis=0))
+# a rank without rows: every rank raises the same error instead of one raising and one hanging
+dist.require_rows_everywhere(3, "single cells")
+try:
+    dist.require_rows_everywhere(0 if r == 1 else 5, "bulk samples")
+    raise SystemExit("expected ValueError on rank " + str(r))
+except ValueError as e:
+    assert "1 of 2 ranks" in str(e), str(e)
 td.destroy_process_group()
 print("rank", r, "ok")
 """

@@ -58,6 +58,16 @@ def all_reduce_np(a):
     return t.cpu().numpy().reshape(a.shape)
 
 
+def require_rows_everywhere(local_rows, what):
+    """Every rank must own at least one row of `what`: the E-step of a rank without rows has
+    nothing to launch, and an exception on that rank alone would leave the others waiting in
+    their collectives.  One small all-reduce decides, and EVERY rank raises the same error."""
+    empty = all_reduce_np(np.array([1.0 if int(local_rows) == 0 else 0.0]))[0]
+    if empty > 0:
+        raise ValueError("%d of %d ranks would hold no %s: use at most as many ranks as there are rows"
+                         % (int(empty), world_size(), what))
+
+
 def gather_rows(a, total_rows=None):
     """Concatenate per-rank row blocks (axis 0) on every rank."""
     d = _dist()

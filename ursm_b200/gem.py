@@ -94,6 +94,10 @@ class LogitNormalGEM(object):
         else:
             self.BKexpr = None
 
+        if self.hasSC:
+            dist.require_rows_everywhere(self.L_local, "single cells")
+        if self.hasBK:
+            dist.require_rows_everywhere(self.M_local, "bulk samples")
         # the device shards exist from here on: the counts are uploaded once, parameter
         # initialisation (below) and the samplers (init_gibbs) work on the same copy
         self._shard_SC = self._shard_BK = None
