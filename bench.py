@@ -508,9 +508,17 @@ def run_c1(verbose=False):
         t0 = time.perf_counter()
         gem = scUnif.main(argv)
         times.append(time.perf_counter() - t0)
+    # the README's usage example / CLI defaults (BASELINE.json configs[0]): 50 / 50 / 50
+    argv50 = list(argv)
+    for flag, val in (("-burnin", "50"), ("-sample", "50"), ("-EM_maxiter", "50")):
+        argv50[argv50.index(flag) + 1] = val
+    t0 = time.perf_counter()
+    gem50 = scUnif.main(argv50)
+    t50 = time.perf_counter() - t0
     for h in list(logging.getLogger("").handlers):
         logging.getLogger("").removeHandler(h)
-    out = {"config": "make run: K=3, 50 cells + 50 bulk x 100 genes, burnin 10 / sample 20 / "
+    out = {"cli_s_burnin50_sample50_EM50": t50, "em_iterations_50_50_50": int(len(gem50.path_elbo)),
+           "config": "make run: K=3, 50 cells + 50 bulk x 100 genes, burnin 10 / sample 20 / "
                      "EM_maxiter 10, bulk mean update (CLI default)",
            "cli_s_first_call": times[0], "cli_s": float(min(times[1:])),
            "elbo_last": float(gem.path_elbo[-1]), "em_iterations": int(len(gem.path_elbo)),
