@@ -422,6 +422,17 @@ def run_workload(name, cfg, args, steps, warmup, world, rank, flush, want_e2e, e
         "kernel_ms": {"sc_gibbs": float(np.mean(sc_ms)) if sc_ms else None,
                       "bk_estep": float(np.mean(bk_ms)) if bk_ms else None},
         "mle_outer_iters_per_step": (float(np.mean([max(o) for o in outer])) if outer else 0.0),
+        # the M-step's streaming pass reads one E[S] counter (1 B at sample <= 255, else
+        # 2 B) per cell x gene of the still-active columns per outer iteration.  Lower bound on its
+        # rate: counters of every column's own iterations / the WHOLE M-step time (trial steps,
+        # gradient and host parts included)
+        "mstep_stream": ({
+            "bytes_per_counter": 1 if sample <= 255 else 2,
+            "counter_bytes_read_per_step": float(np.mean([sum(o) for o in outer])) * (Ll / max(K, 1)) * N
+            * (1 if sample <= 255 else 2),
+            "gbs_over_whole_mstep": float(np.mean([sum(o) for o in outer])) * (Ll / max(K, 1)) * N
+            * (1 if sample <= 255 else 2) / (m_ms * 1e-3) / 1e9,
+            "peak_gbs": load_peaks()[0]} if outer and m_ms > 0 else None),
         "mle_outer_iters_by_column_last_step": outer[-1] if outer else None,
         "mle_halvings_per_step": (gem.mle.nhalvings - halv0) / float(steps),
         "sc_geometry": gem.Gibbs_SC.geometry() if gem.hasSC else None,
@@ -590,7 +601,7 @@ def gpu_run(args, cfg):
             r = run_workload(wl, c, args, st, 1, world, rank, flush, e2e_st > 0, max(e2e_st, 1))
             keep = ("desc", "cells_total", "bulk_total", "K", "N", "burnin", "sample", "steps",
                     "s_per_em_iter", "value", "estep_ms", "mstep_ms", "kernel_ms",
-                    "mle_outer_iters_per_step", "sc_geometry")
+                    "mle_outer_iters_per_step", "mstep_stream", "sc_geometry")
             ent = {k: r[k] for k in keep}
             ent["unit"] = UNIT
             if r["e2e"]:
@@ -679,6 +690,7 @@ def gpu_run(args, cfg):
         "s_per_em_iter": main["s_per_em_iter"], "wall_ms_per_step": main["wall_ms_per_step"],
         "estep_ms": main["estep_ms"], "mstep_ms": main["mstep_ms"],
         "mle_outer_iters_per_step": main["mle_outer_iters_per_step"],
+        "mstep_stream": main["mstep_stream"],
         "mle_outer_iters_by_column_last_step": main["mle_outer_iters_by_column_last_step"],
         "mle_halvings_per_step": main["mle_halvings_per_step"],
         "kernel_ms": main["kernel_ms"], "sc_geometry": main["sc_geometry"],
